@@ -1,0 +1,214 @@
+"""ORACLE (test infrastructure, NOT product code): ctypes front-end of libur3e_oracle.so.
+
+`Model(xml_path)` parses the MJCF with oracle/mjcf_model.py, uploads the arrays into the C
+oracle and runs mj_setConst's restatement; `Data(model)` exposes the MuJoCo-named arrays as
+numpy views.  Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
+Parity status: UNPINNED against a real MuJoCo build (see ur3e_oracle.h).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import mjcf_model
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+INT_FIELDS = """body_parentid body_rootid body_weldid body_jntadr body_jntnum body_dofadr body_dofnum
+jnt_type jnt_bodyid jnt_qposadr jnt_dofadr jnt_limited dof_bodyid dof_jntid dof_parentid geom_type geom_bodyid
+site_bodyid tendon_adr tendon_num wrap_jnt eq_type eq_obj1id eq_obj2id actuator_trntype actuator_trnid
+actuator_ctrllimited actuator_forcelimited pair_geom1 pair_geom2 pair_condim""".split()
+DBL_FIELDS = """body_pos body_quat body_ipos body_iquat body_mass body_inertia body_invweight0 jnt_pos jnt_axis
+jnt_range jnt_stiffness jnt_margin jnt_solref jnt_solimp qpos0 qpos_spring dof_armature dof_damping dof_frictionloss
+dof_invweight0 dof_solref dof_solimp geom_pos geom_quat geom_size site_pos site_quat wrap_coef tendon_invweight0
+eq_data eq_solref eq_solimp actuator_gainprm actuator_biasprm actuator_ctrlrange actuator_forcerange actuator_gear
+pair_friction pair_solref pair_solimp pair_margin pair_gap key_qpos key_qvel""".split()
+
+
+class OContact(C.Structure):
+    _fields_ = [("dist", C.c_double), ("pos", C.c_double * 3), ("frame", C.c_double * 9), ("friction", C.c_double * 5),
+                ("solref", C.c_double * 2), ("solimp", C.c_double * 5), ("mu", C.c_double), ("includemargin", C.c_double),
+                ("geom1", C.c_int), ("geom2", C.c_int), ("dim", C.c_int), ("efc_address", C.c_int)]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "_build", "libur3e_oracle.so")
+    src = [os.path.join(_HERE, f) for f in ("ur3e_oracle.c", "ur3e_oracle.h")]
+    if force or not os.path.exists(so) or any(os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        vp, cp, ip, dp = C.c_void_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_double)
+        L.o_model_new.restype = vp; L.o_model_new.argtypes = [ip, dp]
+        L.o_model_set_int.argtypes = [vp, cp, ip, C.c_int]; L.o_model_set_dbl.argtypes = [vp, cp, dp, C.c_int]
+        L.o_model_get_dbl.argtypes = [vp, cp, C.POINTER(dp)]
+        L.o_model_free.argtypes = [vp]; L.o_set_const.argtypes = [vp]
+        L.o_model_meaninertia.restype = C.c_double; L.o_model_meaninertia.argtypes = [vp]
+        L.o_data_new.restype = vp; L.o_data_new.argtypes = [vp]; L.o_data_free.argtypes = [vp]
+        L.o_data_get_dbl.argtypes = [vp, vp, cp, C.POINTER(dp), ip]; L.o_data_get_int.argtypes = [vp, vp, cp, C.POINTER(ip), ip]
+        L.o_data_contacts.restype = C.POINTER(OContact); L.o_data_contacts.argtypes = [vp]
+        L.o_data_info.argtypes = [vp, C.c_int]; L.o_data_time.restype = C.c_double; L.o_data_time.argtypes = [vp]
+        for f in ("o_reset_data", "o_forward", "o_step"):
+            getattr(L, f).argtypes = [vp, vp]
+        L.o_step_n.argtypes = [vp, vp, C.c_int]
+        L.o_jac.argtypes = [vp, vp, dp, dp, dp, C.c_int]; L.o_jac_site.argtypes = [vp, vp, dp, dp, C.c_int]
+        L.o_object_velocity_site.argtypes = [vp, vp, C.c_int, dp, C.c_int]
+        L.o_fullM.argtypes = [vp, vp, dp]
+        L.o_pid_task_ctrl.argtypes = [vp, vp, C.c_int, dp, dp, dp]; L.o_pd_joint_ctrl.argtypes = [vp, vp, dp, dp, dp, dp]
+        L.o_rot_err.argtypes = [dp, dp, dp]
+        _LIB = L
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Model:
+    def __init__(self, xml_path):
+        L = lib()
+        m = mjcf_model.load_mjcf(xml_path)
+        self.py = m
+        self.names = m["names"]
+        pc = m["pair_candidates"]
+        m["npair"] = len(pc)
+        m["pair_geom1"] = np.array([r["g1"] for r in pc], dtype=np.int32)
+        m["pair_geom2"] = np.array([r["g2"] for r in pc], dtype=np.int32)
+        m["pair_condim"] = np.array([r["condim"] for r in pc], dtype=np.int32)
+        m["pair_friction"] = np.array([r["friction"] for r in pc], dtype=np.float64).reshape(len(pc), 5)
+        m["pair_solref"] = np.array([r["solref"] for r in pc], dtype=np.float64).reshape(len(pc), 2)
+        m["pair_solimp"] = np.array([r["solimp"] for r in pc], dtype=np.float64).reshape(len(pc), 5)
+        m["pair_margin"] = np.array([r["margin"] for r in pc], dtype=np.float64)
+        m["pair_gap"] = np.array([r["gap"] for r in pc], dtype=np.float64)
+        m["nwrap"] = len(m["wrap_jnt"])
+        m["body_invweight0"] = np.zeros(2 * m["nbody"]); m["dof_invweight0"] = np.zeros(m["nv"])
+        m["tendon_invweight0"] = np.zeros(m["ntendon"])
+        sizes = np.array([m[k] for k in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "neq", "ntendon", "nwrap", "npair", "nkey")], dtype=np.int32)
+        o = m["opt"]
+        opt = np.array([o["timestep"], *o["gravity"], o["impratio"], o["tolerance"], o["ls_tolerance"],
+                        1.0 if o["cone"] == "elliptic" else 0.0, o["iterations"], o["ls_iterations"]], dtype=np.float64)
+        self.ptr = L.o_model_new(_ip(sizes), _dp(opt))
+        for f in INT_FIELDS:
+            a = np.ascontiguousarray(m[f], dtype=np.int32).ravel()
+            rc = L.o_model_set_int(self.ptr, f.encode(), _ip(a), a.size)
+            assert rc == 0, (f, rc, a.size)
+        for f in DBL_FIELDS:
+            a = np.ascontiguousarray(m[f], dtype=np.float64).ravel()
+            rc = L.o_model_set_dbl(self.ptr, f.encode(), _dp(a), a.size)
+            assert rc == 0, (f, rc, a.size)
+        L.o_set_const(self.ptr)
+        for k in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "neq", "ntendon", "npair", "nkey"):
+            setattr(self, k, int(m[k]))
+        self.timestep = o["timestep"]
+        self.meaninertia = L.o_model_meaninertia(self.ptr)
+
+    def arr(self, name):
+        """numpy view of a float64 model array held by the C oracle (post set_const)."""
+        p = C.POINTER(C.c_double)()
+        n = lib().o_model_get_dbl(self.ptr, name.encode(), C.byref(p))
+        assert n >= 0, name
+        return np.ctypeslib.as_array(p, shape=(max(n, 1),))[:n]
+
+    def id(self, kind, name):
+        return self.names[kind].index(name)
+
+    def key(self, name):
+        k = self.names["key"].index(name)
+        return self.py["key_qpos"][k].copy(), self.py["key_qvel"][k].copy()
+
+    def __del__(self):
+        try:
+            lib().o_model_free(self.ptr)
+        except Exception:
+            pass
+
+
+class Data:
+    def __init__(self, model):
+        self.m = model
+        self.ptr = lib().o_data_new(model.ptr)
+        self._cache = {}
+
+    def arr(self, name):
+        if name not in self._cache:
+            p = C.POINTER(C.c_double)(); n = C.c_int()
+            if lib().o_data_get_dbl(self.m.ptr, self.ptr, name.encode(), C.byref(p), C.byref(n)) == 0:
+                self._cache[name] = np.ctypeslib.as_array(p, shape=(max(n.value, 1),))[:n.value]
+            else:
+                q = C.POINTER(C.c_int)()
+                assert lib().o_data_get_int(self.m.ptr, self.ptr, name.encode(), C.byref(q), C.byref(n)) == 0, name
+                self._cache[name] = np.ctypeslib.as_array(q, shape=(max(n.value, 1),))[:n.value]
+        return self._cache[name]
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name in ("m", "ptr"):
+            raise AttributeError(name)
+        return self.arr(name)
+
+    # scalars
+    @property
+    def ncon(self): return lib().o_data_info(self.ptr, 0)
+    @property
+    def nefc(self): return lib().o_data_info(self.ptr, 1)
+    @property
+    def solver_iter(self): return lib().o_data_info(self.ptr, 2)
+    @property
+    def warn_bad(self): return lib().o_data_info(self.ptr, 3)
+    @property
+    def time(self): return lib().o_data_time(self.ptr)
+
+    def contacts(self):
+        c = lib().o_data_contacts(self.ptr)
+        return [c[i] for i in range(self.ncon)]
+
+    def reset(self): lib().o_reset_data(self.m.ptr, self.ptr)
+    def forward(self): lib().o_forward(self.m.ptr, self.ptr)
+    def step(self, n=1): lib().o_step_n(self.m.ptr, self.ptr, n)
+
+    def set_state(self, qpos, qvel):
+        self.arr("qpos")[:] = qpos; self.arr("qvel")[:] = qvel
+
+    def fullM(self):
+        nv = self.m.nv; out = np.zeros((nv, nv)); lib().o_fullM(self.m.ptr, self.ptr, _dp(out)); return out
+
+    def jac_site(self, site):
+        nv = self.m.nv; jp = np.zeros((3, nv)); jr = np.zeros((3, nv))
+        lib().o_jac_site(self.m.ptr, self.ptr, _dp(jp), _dp(jr), site); return jp, jr
+
+    def jac(self, point, body):
+        nv = self.m.nv; jp = np.zeros((3, nv)); jr = np.zeros((3, nv)); pt = np.ascontiguousarray(point, dtype=np.float64)
+        lib().o_jac(self.m.ptr, self.ptr, _dp(jp), _dp(jr), _dp(pt), body); return jp, jr
+
+    def site_velocity(self, site, local=0):
+        out = np.zeros(6); lib().o_object_velocity_site(self.m.ptr, self.ptr, site, _dp(out), local); return out
+
+    def pid_task_ctrl(self, tcp_site, traj7, gains12):
+        u = np.zeros(7); t = np.ascontiguousarray(traj7, dtype=np.float64); g = np.ascontiguousarray(gains12, dtype=np.float64)
+        lib().o_pid_task_ctrl(self.m.ptr, self.ptr, tcp_site, _dp(t), _dp(g), _dp(u)); return u
+
+    def pd_joint_ctrl(self, target6, kp6, kd6):
+        u = np.zeros(6)
+        a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (target6, kp6, kd6))
+        lib().o_pd_joint_ctrl(self.m.ptr, self.ptr, _dp(a), _dp(b), _dp(c), _dp(u)); return u
+
+    def __del__(self):
+        try:
+            lib().o_data_free(self.ptr)
+        except Exception:
+            pass
+
+
+def rot_err(xmat9, rotvec3):
+    out = np.zeros(3); a = np.ascontiguousarray(xmat9, dtype=np.float64).ravel(); b = np.ascontiguousarray(rotvec3, dtype=np.float64)
+    lib().o_rot_err(_dp(a), _dp(b), _dp(out)); return out
