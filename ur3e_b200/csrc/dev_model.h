@@ -1,0 +1,95 @@
+// Flat device model + env configuration consumed by the fused step kernel (engine.cuh).
+// POD only: uploaded once per batch with cudaMemcpy, read through the read-only cache.
+#pragma once
+#include <cstdint>
+
+namespace ur3e {
+
+constexpr int MAXB = 26;     // bodies incl. world
+constexpr int MAXV = 20;     // dofs
+constexpr int MAXQ = 21;     // generalized positions
+constexpr int MAXU = 7;      // actuators
+constexpr int MAXG = 8;      // collidable primitive geoms
+constexpr int MAXPAIR = 16;  // candidate geom pairs
+constexpr int MAXEQ = 3;     // equality constraints
+constexpr int MAXSITE = 4;   // tracked sites (tcp, handle, pad)
+constexpr int MAXNM = 128;   // nnz of lower-triangular M
+constexpr int MAXKEY = 2;
+constexpr int MAXCON = 32;   // contacts per env
+constexpr int MAXEFC = 112;  // constraint rows per env
+
+enum JointKind { JK_NONE = 0, JK_HINGE = 1, JK_FREE = 2 };
+enum GeomKind { GK_PLANE = 0, GK_BOX = 1 };
+enum EqKind { EK_CONNECT = 0, EK_JOINT = 1 };
+
+// controller evaluated inside the kernel (reference controller/controller_func.py)
+enum CtrlMode {
+  CTRL_RAW = 0,       // action = actuator ctrl vector (imitation_env_direct.py:90)
+  CTRL_PD_JOINT = 1,  // pd_joint_ctrl + move_j.get_joint_delta (controller_func.py:128-167, move_j.py:14-38)
+  CTRL_PID_TASK = 2,  // pid_task_ctrl, action = full 7-vector trajectory point (move_l_task.py:55-69)
+  CTRL_PID_TASK_ENV = 3,  // pid_task_ctrl, action = [x,y,z,grip], fixed tool orientation (ur3e_env2.py:72-82)
+  CTRL_PINV = 4       // move_l.ctrl: pinv(J) IK + two joint PDs (move_l.py:15-78)
+};
+enum ObsKind { OBS_STATE = 0 /* qpos,qvel */, OBS_V2 = 1 /* 24 */, OBS_V0 = 2 /* 13 */, OBS_DIRECT = 3 /* 13 */ };
+enum RewardKind { REW_NONE = 0, REW_V2 = 1, REW_V0 = 2, REW_MINUS1 = 3 };
+enum TermKind { TERM_NONE = 0, TERM_V2 = 1, TERM_V0 = 2 };
+enum ResetNoise { NOISE_NONE = 0, NOISE_LOW = 1, NOISE_MED = 2, NOISE_HIGH = 3 };
+
+template <typename Real>
+struct DevModel {
+  // sizes
+  int nq, nv, nu, nbody, nlevel, ngeom, npair, neq, nsite, nM, nkey, nfl;
+  int has_damping, pad_;
+  Real timestep, gravity[3], impratio, meaninertia;
+  // bodies (index 0 = world)
+  int body_parent[MAXB], body_level[MAXB], body_jkind[MAXB], body_qadr[MAXB], body_dadr[MAXB], body_lastdof[MAXB], body_root[MAXB];
+  uint32_t body_dofmask[MAXB];  // bit d set when dof d moves the body
+  Real body_pos[MAXB][3], body_quat[MAXB][4], body_ipos[MAXB][3], body_iquat[MAXB][4], body_mass[MAXB], body_inertia[MAXB][3];
+  Real body_invw[MAXB][2];
+  Real jnt_pos[MAXB][3], jnt_axis[MAXB][3], jnt_q0[MAXB];  // the (single) joint of each body
+  // dofs
+  int dof_body[MAXV], dof_parent[MAXV], dof_qadr[MAXV], dof_limited[MAXV], dof_free_k[MAXV];  // free_k: -1 hinge, 0..5 component of a free joint
+  Real dof_armature[MAXV], dof_damping[MAXV], dof_frictionloss[MAXV], dof_invw[MAXV], dof_stiffness[MAXV], dof_springref[MAXV];
+  Real dof_range[MAXV][2], dof_margin[MAXV], dof_lim_solref[MAXV][2], dof_lim_solimp[MAXV][5], dof_fl_solref[MAXV][2], dof_fl_solimp[MAXV][5];
+  int fl_dof[MAXV];  // dofs with frictionloss, in order
+  // lower-triangular sparsity of M: (i, j) with j ancestor-or-self of i
+  int M_i[MAXNM], M_j[MAXNM];
+  int tri_ab[(MAXV + 1) * (MAXV + 2) / 2];  // (a << 8 | b), b <= a, row-major lower triangle of the (nv+1)^2 augmented matrix
+  // collidable geoms
+  int geom_body[MAXG], geom_kind[MAXG];
+  Real geom_pos[MAXG][3], geom_quat[MAXG][4], geom_size[MAXG][3], geom_rbound[MAXG];
+  // candidate pairs (geom1 = plane for plane-box)
+  int pair_g1[MAXPAIR], pair_g2[MAXPAIR], pair_src_g1[MAXPAIR], pair_src_g2[MAXPAIR];
+  Real pair_friction[MAXPAIR][2], pair_solref[MAXPAIR][2], pair_solimp[MAXPAIR][5], pair_margin[MAXPAIR], pair_includemargin[MAXPAIR], pair_invw[MAXPAIR];
+  // equality
+  int eq_kind[MAXEQ], eq_o1[MAXEQ], eq_o2[MAXEQ];
+  Real eq_data[MAXEQ][6], eq_solref[MAXEQ][2], eq_solimp[MAXEQ][5], eq_invw[MAXEQ];
+  // tracked sites
+  int site_body[MAXSITE];
+  Real site_pos[MAXSITE][3], site_quat[MAXSITE][4];
+  // actuators: force = gain*ctrl + b0 + b1*len + b2*vel ; moment over at most two dofs
+  int act_dof[MAXU][2], act_ctrllimited[MAXU], act_forcelimited[MAXU];
+  Real act_coef[MAXU][2], act_gain[MAXU], act_bias[MAXU][3], act_ctrlrange[MAXU][2], act_forcerange[MAXU][2];
+  // reset
+  Real qpos0[MAXQ], key_qpos[MAXKEY][MAXQ], key_qvel[MAXKEY][MAXV];
+};
+
+template <typename Real>
+struct EnvCfg {
+  int ctrl_mode, obs_kind, reward_kind, term_kind;
+  int frame_skip, act_dim, obs_dim, max_steps;
+  int trunc_after_increment;  // v2 increments t before the truncation test (ur3e_env2.py:89-92); others test first
+  int reset_key, reset_noise, auto_reset;
+  int site_tcp, site_mug, site_pad, body_mug, body_ghost, body_lpad, body_rpad, finger_q;  // model indices (-1 when absent)
+  int clip_action, pad_;
+  Real gains[24];          // CTRL_PID_TASK*: kp_pos[3] kd_pos[3] kp_rot[3] kd_rot[3]; CTRL_PD_JOINT: kp[6] kd[6]; CTRL_PINV: kp_p[6] kd_p[6] kp_r[6] kd_r[6]
+  Real tool_rotvec[3];     // ur3e_env2.py:74
+  Real act_low[8], act_high[8];
+  Real mug_size[3];
+  Real ghost_pos[3];
+  Real topple_z;           // max(size_x, size_y) of the mug box (gym_utils.py:8-17)
+};
+
+constexpr int CACHE_SIZE = 3 + 9 + 36 + 6;  // tcp_pos, tcp_mat, J_arm (6x6: rows px,py,pz,rx,ry,rz), qfrc_bias[:6]
+
+}  // namespace ur3e

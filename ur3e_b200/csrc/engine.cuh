@@ -1,0 +1,911 @@
+// Fused per-environment simulation step for the UR3e + 2F85 (+ mug) scenes: one environment per warp,
+// all per-substep state in a shared-memory arena (see DESIGN.md "kernel").
+//
+// Replaces, for one environment, the reference's  controller -> mj_step x frame_skip -> obs/reward/done
+// path (reference gymnasium_env/envs/ur3e_env2.py:72-99; controller/controller_func.py:68-117,128-167;
+// mujoco mj_step restated in SURVEY App. B).  This file is written against warp_model.cuh and contains
+// no CUDA-only constructs, so tests/hostcheck can compile it on the CPU to debug the mathematics.
+#pragma once
+#include "dev_model.h"
+#include "warp_model.cuh"
+
+namespace ur3e {
+
+template <int NB_, int NV_, int NQ_, int NU_, int NG_, int NPAIR_, int MAXCON_, int MAXEFC_>
+struct Dims {
+  static constexpr int NB = NB_, NV = NV_, NQ = NQ_, NU = NU_, NG = NG_ > 0 ? NG_ : 1, NPAIR = NPAIR_ > 0 ? NPAIR_ : 1;
+  static constexpr int MAXCON = MAXCON_ > 0 ? MAXCON_ : 1, MAXEFC = MAXEFC_ > 0 ? MAXEFC_ : 1;
+  static constexpr bool HAS_CONTACT = MAXCON_ > 0;
+  static constexpr int NS = MAXSITE;
+};
+using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // assets/ur3e_raw.xml
+using DimsGrip = Dims<23, 14, 14, 7, 6, 12, 16, 72>;    // assets/ur3e_2f85.xml
+using DimsMain = Dims<25, 20, 21, 7, 7, 16, 32, 112>;   // assets/main.xml
+
+constexpr int STAGE_PTS = 8;  // contact points a pair can emit
+
+enum RowType { ROW_EQ = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_CON_N = 3, ROW_CON_T1 = 4, ROW_CON_T2 = 5 };
+
+template <typename Real, typename D>
+struct Arena {
+  Real qpos[D::NQ], qvel[D::NV], qacc[D::NV], qacc_ws[D::NV], ctrl[D::NU], act_force[D::NU];
+  Real xpos[D::NB][3], xquat[D::NB][4], xmat[D::NB][9], xipos[D::NB][3];
+  Real cdof[D::NV][6];
+  Real M[D::NV][D::NV];
+  Real H[D::NV + 1][D::NV + 1];
+  Real qfrc_smooth[D::NV], qfrc_bias[D::NV], qfrc_constraint[D::NV], grad[D::NV], search[D::NV], Ma[D::NV], Mv[D::NV];
+  Real geom_xpos[D::NG][3], geom_xmat[D::NG][9], site_xpos[D::NS][3], site_xmat[D::NS][9], site_velp[D::NS][3];
+  Real con_pos[D::MAXCON][3], con_frame[D::MAXCON][9], con_dist[D::MAXCON], con_mu[D::MAXCON], con_H[D::MAXCON][6];
+  Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_R[D::MAXEFC], efc_force[D::MAXEFC], efc_jar[D::MAXEFC], efc_jv[D::MAXEFC],
+      efc_fl[D::MAXEFC], efc_Dact[D::MAXEFC];
+  int con_pair[D::MAXCON], con_row[D::MAXCON];
+  int efc_type[D::MAXEFC], efc_id[D::MAXEFC];
+  int stage_n[D::NPAIR], stage_off[D::NPAIR];
+  int ncon, nefc, ne, nf, nl, overflow, solver_iter, bad;
+  union {
+    struct { Real cinert[D::NB][10], crb[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6], fbuf[D::NV][6]; } dyn;
+    Real stage[D::NPAIR][STAGE_PTS][7];  // pos 3, normal 3, dist
+    Real efc_J[D::MAXEFC][D::NV];
+  } u;
+  Real cache[CACHE_SIZE];
+};
+
+// ---------------------------------------------------------------- scalar math
+template <typename Real> struct Num;
+template <> struct Num<float> {
+  static UR3E_HD float sqrt(float x) { return ::sqrtf(x); }
+  static UR3E_HD float sin(float x) { return ::sinf(x); }
+  static UR3E_HD float cos(float x) { return ::cosf(x); }
+  static UR3E_HD float atan2(float y, float x) { return ::atan2f(y, x); }
+  static UR3E_HD float pow(float x, float y) { return ::powf(x, y); }
+  static UR3E_HD float exp(float x) { return ::expf(x); }
+  static UR3E_HD float tanh(float x) { return ::tanhf(x); }
+  static UR3E_HD float abs(float x) { return ::fabsf(x); }
+  static constexpr float minval = 1e-15f, big = 1e30f;
+};
+template <> struct Num<double> {
+  static UR3E_HD double sqrt(double x) { return ::sqrt(x); }
+  static UR3E_HD double sin(double x) { return ::sin(x); }
+  static UR3E_HD double cos(double x) { return ::cos(x); }
+  static UR3E_HD double atan2(double y, double x) { return ::atan2(y, x); }
+  static UR3E_HD double pow(double x, double y) { return ::pow(x, y); }
+  static UR3E_HD double exp(double x) { return ::exp(x); }
+  static UR3E_HD double tanh(double x) { return ::tanh(x); }
+  static UR3E_HD double abs(double x) { return ::fabs(x); }
+  static constexpr double minval = 1e-15, big = 1e300;
+};
+template <typename Real> UR3E_HD Real rmax(Real a, Real b) { return a > b ? a : b; }
+template <typename Real> UR3E_HD Real rmin(Real a, Real b) { return a < b ? a : b; }
+template <typename Real> UR3E_HD Real dot3(const Real* a, const Real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename Real> UR3E_HD void cross3(Real* r, const Real* a, const Real* b) {
+  Real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename Real> UR3E_HD void quat_mul(Real* r, const Real* a, const Real* b) {
+  Real w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3], x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  Real y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1], z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+template <typename Real> UR3E_HD void quat_normalize(Real* q) {
+  Real n = Num<Real>::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < Num<Real>::minval) { q[0] = 1; q[1] = q[2] = q[3] = 0; } else { Real s = Real(1) / n; q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
+}
+template <typename Real> UR3E_HD void quat2mat(Real* m, const Real* q) {
+  Real w = q[0], x = q[1], y = q[2], z = q[3];
+  m[0] = w * w + x * x - y * y - z * z; m[1] = 2 * (x * y - w * z); m[2] = 2 * (x * z + w * y);
+  m[3] = 2 * (x * y + w * z); m[4] = w * w - x * x + y * y - z * z; m[5] = 2 * (y * z - w * x);
+  m[6] = 2 * (x * z - w * y); m[7] = 2 * (y * z + w * x); m[8] = w * w - x * x - y * y + z * z;
+}
+template <typename Real> UR3E_HD void mat_vec3(Real* r, const Real* m, const Real* v) {
+  Real x = m[0] * v[0] + m[1] * v[1] + m[2] * v[2], y = m[3] * v[0] + m[4] * v[1] + m[5] * v[2], z = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename Real> UR3E_HD Real normalize3(Real* a) {
+  Real n = Num<Real>::sqrt(dot3(a, a));
+  if (n < Num<Real>::minval) { a[0] = 1; a[1] = 0; a[2] = 0; } else { Real s = Real(1) / n; a[0] *= s; a[1] *= s; a[2] *= s; }
+  return n;
+}
+// spatial vectors: [rotational(3); translational(3)] about the tree reference point, world axes
+template <typename Real> UR3E_HD void mul_inert(Real* r, const Real* i, const Real* v) {
+  Real r0 = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  Real r1 = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  Real r2 = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  Real r3 = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  Real r4 = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  Real r5 = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+  r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4; r[5] = r5;
+}
+template <typename Real> UR3E_HD void cross_motion(Real* r, const Real* vel, const Real* v) {
+  Real a[3], b[3], c[3];
+  cross3(a, vel, v); cross3(b, vel, v + 3); cross3(c, vel + 3, v);
+  r[0] = a[0]; r[1] = a[1]; r[2] = a[2]; r[3] = b[0] + c[0]; r[4] = b[1] + c[1]; r[5] = b[2] + c[2];
+}
+template <typename Real> UR3E_HD void cross_force(Real* r, const Real* vel, const Real* f) {
+  Real a[3], b[3], c[3];
+  cross3(a, vel, f); cross3(b, vel + 3, f + 3); cross3(c, vel, f + 3);
+  r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
+}
+
+// ---------------------------------------------------------------- kinematics
+template <typename Real, typename D>
+UR3E_HD void fk_body(const DevModel<Real>& m, Arena<Real, D>& s, int b) {
+  int p = m.body_parent[b], jk = m.body_jkind[b];
+  Real pos[3], quat[4];
+  if (jk == JK_FREE) {
+    int qa = m.body_qadr[b], da = m.body_dadr[b];
+    for (int k = 0; k < 3; ++k) pos[k] = s.qpos[qa + k];
+    for (int k = 0; k < 4; ++k) quat[k] = s.qpos[qa + 3 + k];
+    quat_normalize(quat);
+    Real R[9]; quat2mat(R, quat);
+    for (int i = 0; i < 3; ++i) {
+      Real* ct = s.cdof[da + i]; Real* cr = s.cdof[da + 3 + i];
+      for (int k = 0; k < 6; ++k) { ct[k] = 0; cr[k] = 0; }
+      ct[3 + i] = 1;                                            // translation along world axis i
+      cr[0] = R[i]; cr[1] = R[3 + i]; cr[2] = R[6 + i];         // rotation about body axis i, through the reference point
+    }
+  } else {
+    Real v[3];
+    mat_vec3(v, s.xmat[p], m.body_pos[b]);
+    for (int k = 0; k < 3; ++k) pos[k] = s.xpos[p][k] + v[k];
+    quat_mul(quat, s.xquat[p], m.body_quat[b]);
+    if (jk == JK_HINGE) {
+      Real R0[9], anchor[3], axis[3], vec[3];
+      quat2mat(R0, quat);
+      mat_vec3(vec, R0, m.jnt_pos[b]);
+      for (int k = 0; k < 3; ++k) anchor[k] = pos[k] + vec[k];
+      mat_vec3(axis, R0, m.jnt_axis[b]);
+      Real ang = s.qpos[m.body_qadr[b]] - m.jnt_q0[b], sn = Num<Real>::sin(ang * Real(0.5)), cs = Num<Real>::cos(ang * Real(0.5));
+      Real ql[4] = {cs, m.jnt_axis[b][0] * sn, m.jnt_axis[b][1] * sn, m.jnt_axis[b][2] * sn};
+      quat_mul(quat, quat, ql);
+      quat_normalize(quat);
+      Real R1[9]; quat2mat(R1, quat);
+      mat_vec3(vec, R1, m.jnt_pos[b]);
+      for (int k = 0; k < 3; ++k) pos[k] = anchor[k] - vec[k];
+      const Real* ref = s.xpos[m.body_root[b]];
+      Real off[3] = {ref[0] - anchor[0], ref[1] - anchor[1], ref[2] - anchor[2]};
+      Real* c = s.cdof[m.body_dadr[b]];
+      c[0] = axis[0]; c[1] = axis[1]; c[2] = axis[2];
+      cross3(c + 3, axis, off);
+    } else {
+      quat_normalize(quat);
+    }
+  }
+  for (int k = 0; k < 3; ++k) s.xpos[b][k] = pos[k];
+  for (int k = 0; k < 4; ++k) s.xquat[b][k] = quat[k];
+  quat2mat(s.xmat[b], quat);
+  Real v[3];
+  mat_vec3(v, s.xmat[b], m.body_ipos[b]);
+  for (int k = 0; k < 3; ++k) s.xipos[b][k] = pos[k] + v[k];
+}
+
+template <typename Real, typename D>
+UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
+  IF_LANE0 {
+    for (int k = 0; k < 3; ++k) { s.xpos[0][k] = 0; s.xipos[0][k] = 0; }
+    s.xquat[0][0] = 1; s.xquat[0][1] = s.xquat[0][2] = s.xquat[0][3] = 0;
+    for (int k = 0; k < 9; ++k) s.xmat[0][k] = (k % 4 == 0) ? Real(1) : Real(0);
+  }
+  WARP_SYNC();
+  for (int lev = 1; lev < m.nlevel; ++lev) {
+    WARP_FOR(b, m.nbody) if (m.body_level[b] == lev) fk_body(m, s, b);
+    WARP_SYNC();
+  }
+  // geoms and tracked sites
+  WARP_FOR(i, m.ngeom + m.nsite) {
+    if (i < m.ngeom) {
+      int b = m.geom_body[i]; Real v[3], q[4];
+      mat_vec3(v, s.xmat[b], m.geom_pos[i]);
+      for (int k = 0; k < 3; ++k) s.geom_xpos[i][k] = s.xpos[b][k] + v[k];
+      quat_mul(q, s.xquat[b], m.geom_quat[i]); quat2mat(s.geom_xmat[i], q);
+    } else {
+      int j = i - m.ngeom, b = m.site_body[j]; Real v[3], q[4];
+      mat_vec3(v, s.xmat[b], m.site_pos[j]);
+      for (int k = 0; k < 3; ++k) s.site_xpos[j][k] = s.xpos[b][k] + v[k];
+      quat_mul(q, s.xquat[b], m.site_quat[j]); quat2mat(s.site_xmat[j], q);
+    }
+  }
+  WARP_SYNC();
+}
+
+// ---------------------------------------------------------------- CRBA + RNE
+template <typename Real, typename D>
+UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
+  const int nb = m.nbody, nv = m.nv;
+  auto& y = s.u.dyn;
+  // body inertias about the tree reference point + body velocities (sum over the dof chain)
+  WARP_FOR(b, nb) {
+    Real* ci = y.cinert[b];
+    if (b == 0 || m.body_lastdof[b] < 0) { for (int k = 0; k < 10; ++k) ci[k] = 0; for (int k = 0; k < 6; ++k) y.cvel[b][k] = 0; }
+    else {
+      const Real* ref = s.xpos[m.body_root[b]];
+      Real dif[3] = {s.xipos[b][0] - ref[0], s.xipos[b][1] - ref[1], s.xipos[b][2] - ref[2]};
+      Real q[4], R[9]; quat_mul(q, s.xquat[b], m.body_iquat[b]); quat2mat(R, q);
+      const Real* in = m.body_inertia[b]; Real mass = m.body_mass[b];
+      Real t00 = 0, t11 = 0, t22 = 0, t01 = 0, t02 = 0, t12 = 0;
+      for (int k = 0; k < 3; ++k) {
+        t00 += R[k] * in[k] * R[k]; t11 += R[3 + k] * in[k] * R[3 + k]; t22 += R[6 + k] * in[k] * R[6 + k];
+        t01 += R[k] * in[k] * R[3 + k]; t02 += R[k] * in[k] * R[6 + k]; t12 += R[3 + k] * in[k] * R[6 + k];
+      }
+      ci[0] = t00 + mass * (dif[1] * dif[1] + dif[2] * dif[2]); ci[1] = t11 + mass * (dif[0] * dif[0] + dif[2] * dif[2]);
+      ci[2] = t22 + mass * (dif[0] * dif[0] + dif[1] * dif[1]);
+      ci[3] = t01 - mass * dif[0] * dif[1]; ci[4] = t02 - mass * dif[0] * dif[2]; ci[5] = t12 - mass * dif[1] * dif[2];
+      ci[6] = mass * dif[0]; ci[7] = mass * dif[1]; ci[8] = mass * dif[2]; ci[9] = mass;
+      Real cv[6] = {0, 0, 0, 0, 0, 0};
+      for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { Real qd = s.qvel[d]; for (int k = 0; k < 6; ++k) cv[k] += s.cdof[d][k] * qd; }
+      for (int k = 0; k < 6; ++k) y.cvel[b][k] = cv[k];
+    }
+  }
+  WARP_FOR(i, nv * nv) (&s.M[0][0])[i] = 0;
+  WARP_SYNC();
+  // composite inertias: lane k carries component k down the (parent < child) body order
+  WARP_FOR(k, 10) {
+    for (int b = 0; b < nb; ++b) y.crb[b][k] = y.cinert[b][k];
+    for (int b = nb - 1; b > 0; --b) { int p = m.body_parent[b]; if (p > 0) y.crb[p][k] += y.crb[b][k]; }
+  }
+  // cdof_dot = (velocity before the dof) x cdof   (mj_comVel)
+  WARP_FOR(d, nv) {
+    int b = m.dof_body[d], fk = m.dof_free_k[d];
+    Real* cd = y.cdof_dot[d];
+    if (fk >= 0 && fk < 3) { for (int k = 0; k < 6; ++k) cd[k] = 0; }
+    else {
+      Real vel[6];
+      for (int k = 0; k < 6; ++k) vel[k] = y.cvel[m.body_parent[b]][k];
+      if (fk >= 3) { int da = m.body_dadr[b]; for (int i = 0; i < 3; ++i) for (int k = 0; k < 6; ++k) vel[k] += s.cdof[da + i][k] * s.qvel[da + i]; }
+      cross_motion(cd, vel, s.cdof[d]);
+    }
+  }
+  WARP_SYNC();
+  // M: f_i = crb(body_i) cdof_i ; M_ij = cdof_j . f_i
+  WARP_FOR(i, nv) mul_inert(y.fbuf[i], y.crb[m.dof_body[i]], s.cdof[i]);
+  // bias wrench of every body: I a + v x* I v, with a = -g + sum cdof_dot qvel over the chain
+  WARP_FOR(b, nb) {
+    Real* f = y.cfrc[b];
+    if (b == 0 || m.body_lastdof[b] < 0) { for (int k = 0; k < 6; ++k) f[k] = 0; }
+    else {
+      Real a[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
+      for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { Real qd = s.qvel[d]; for (int k = 0; k < 6; ++k) a[k] += y.cdof_dot[d][k] * qd; }
+      Real t1[6], t2[6];
+      mul_inert(f, y.cinert[b], a);
+      mul_inert(t1, y.cinert[b], y.cvel[b]); cross_force(t2, y.cvel[b], t1);
+      for (int k = 0; k < 6; ++k) f[k] += t2[k];
+    }
+  }
+  WARP_SYNC();
+  WARP_FOR(e, m.nM) {
+    int i = m.M_i[e], j = m.M_j[e];
+    Real v = 0; for (int k = 0; k < 6; ++k) v += s.cdof[j][k] * y.fbuf[i][k];
+    if (i == j) v += m.dof_armature[i];
+    s.M[i][j] = v; s.M[j][i] = v;
+  }
+  WARP_FOR(k, 6) { for (int b = nb - 1; b > 0; --b) { int p = m.body_parent[b]; if (p > 0) y.cfrc[p][k] += y.cfrc[b][k]; } }
+  WARP_SYNC();
+  // site linear velocities (mj_objectVelocity, world frame) for the observation
+  WARP_FOR(j, m.nsite) {
+    int b = m.site_body[j];
+    if (m.body_lastdof[b] < 0) { s.site_velp[j][0] = s.site_velp[j][1] = s.site_velp[j][2] = 0; }
+    else {
+      const Real* ref = s.xpos[m.body_root[b]]; const Real* cv = y.cvel[b];
+      Real off[3] = {s.site_xpos[j][0] - ref[0], s.site_xpos[j][1] - ref[1], s.site_xpos[j][2] - ref[2]}, t[3];
+      cross3(t, cv, off);
+      for (int k = 0; k < 3; ++k) s.site_velp[j][k] = cv[3 + k] + t[k];
+    }
+  }
+  // actuator forces
+  WARP_FOR(a, m.nu) {
+    Real c = s.ctrl[a];
+    if (m.act_ctrllimited[a]) c = rmin(rmax(c, m.act_ctrlrange[a][0]), m.act_ctrlrange[a][1]);
+    Real len = 0, vel = 0;
+    for (int k = 0; k < 2; ++k) { int d = m.act_dof[a][k]; if (d >= 0) { len += m.act_coef[a][k] * s.qpos[m.dof_qadr[d]]; vel += m.act_coef[a][k] * s.qvel[d]; } }
+    Real f = m.act_gain[a] * c + m.act_bias[a][0] + m.act_bias[a][1] * len + m.act_bias[a][2] * vel;
+    if (m.act_forcelimited[a]) f = rmin(rmax(f, m.act_forcerange[a][0]), m.act_forcerange[a][1]);
+    s.act_force[a] = f;
+  }
+  WARP_SYNC();
+  WARP_FOR(d, nv) {
+    Real bias = 0; for (int k = 0; k < 6; ++k) bias += s.cdof[d][k] * y.cfrc[m.dof_body[d]][k];
+    s.qfrc_bias[d] = bias;
+    Real f = -m.dof_damping[d] * s.qvel[d];
+    if (m.dof_free_k[d] < 0) f -= m.dof_stiffness[d] * (s.qpos[m.dof_qadr[d]] - m.dof_springref[d]);
+    for (int a = 0; a < m.nu; ++a) for (int k = 0; k < 2; ++k) if (m.act_dof[a][k] == d) f += m.act_coef[a][k] * s.act_force[a];
+    s.qfrc_smooth[d] = f - bias;
+  }
+  WARP_SYNC();
+}
+
+// ---------------------------------------------------------------- collision
+template <typename Real> UR3E_HD void make_frame(Real* f) {
+  normalize3(f);
+  Real* y = f + 3;
+  y[0] = 0; y[1] = 0; y[2] = 0;
+  if (f[1] < Real(0.5) && f[1] > Real(-0.5)) y[1] = 1; else y[2] = 1;
+  Real t = dot3(f, y);
+  for (int k = 0; k < 3; ++k) y[k] -= t * f[k];
+  normalize3(y);
+  cross3(f + 6, f, y);
+}
+
+template <typename Real>
+UR3E_HD int plane_box(const Real* ppos, const Real* pmat, const Real* bpos, const Real* bmat, const Real* size, Real margin, Real (*out)[7]) {
+  Real n[3] = {pmat[2], pmat[5], pmat[8]};
+  Real dif[3] = {bpos[0] - ppos[0], bpos[1] - ppos[1], bpos[2] - ppos[2]};
+  Real cd = dot3(dif, n);
+  int cnt = 0;
+  for (int i = 0; i < 8; ++i) {
+    Real v[3] = {(i & 1) ? size[0] : -size[0], (i & 2) ? size[1] : -size[1], (i & 4) ? size[2] : -size[2]}, c[3];
+    mat_vec3(c, bmat, v);
+    Real ld = dot3(n, c);
+    if (cd + ld > margin || ld > 0) continue;
+    Real dist = cd + ld;
+    for (int k = 0; k < 3; ++k) { out[cnt][k] = c[k] + bpos[k] - n[k] * dist * Real(0.5); out[cnt][3 + k] = n[k]; }
+    out[cnt][6] = dist;
+    if (++cnt >= 4) break;
+  }
+  return cnt;
+}
+
+template <typename Real>
+UR3E_HD int clip_poly(Real* px, Real* py, int n, Real a, Real b, Real c) {
+  Real ox[16], oy[16]; int k = 0;
+  for (int i = 0; i < n; ++i) {
+    int j = (i + 1 == n) ? 0 : i + 1;
+    Real di = a * px[i] + b * py[i] - c, dj = a * px[j] + b * py[j] - c;
+    if (di <= 0) { ox[k] = px[i]; oy[k] = py[i]; ++k; }
+    if ((di < 0 && dj > 0) || (di > 0 && dj < 0)) { Real t = di / (di - dj); ox[k] = px[i] + t * (px[j] - px[i]); oy[k] = py[i] + t * (py[j] - py[i]); ++k; }
+    if (k >= 15) break;
+  }
+  for (int i = 0; i < k; ++i) { px[i] = ox[i]; py[i] = oy[i]; }
+  return k;
+}
+
+// box-box manifold; same rules as the oracle's box_box (oracle/ur3e_oracle.c), normal from box 1 to box 2
+template <typename Real>
+UR3E_HD int box_box(const Real* p1, const Real* R1, const Real* s1, const Real* p2, const Real* R2, const Real* s2, Real margin, Real (*out)[7]) {
+  Real d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, A1[3][3], A2[3][3];
+  for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) { A1[i][k] = R1[3 * k + i]; A2[i][k] = R2[3 * k + i]; }
+  Real AC[3][3];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) AC[i][j] = Num<Real>::abs(dot3(A1[i], A2[j]));
+  Real best = -Num<Real>::big; int code = -1; Real bn[3] = {0, 0, 0};
+  for (int i = 0; i < 3; ++i) {
+    Real t = dot3(d, A1[i]), ra = s1[i], rb = s2[0] * AC[i][0] + s2[1] * AC[i][1] + s2[2] * AC[i][2];
+    Real sep = Num<Real>::abs(t) - ra - rb;
+    if (sep > margin) return 0;
+    if (sep > best) { best = sep; code = i; Real sg = t < 0 ? Real(-1) : Real(1); for (int k = 0; k < 3; ++k) bn[k] = sg * A1[i][k]; }
+  }
+  for (int j = 0; j < 3; ++j) {
+    Real t = dot3(d, A2[j]), ra = s1[0] * AC[0][j] + s1[1] * AC[1][j] + s1[2] * AC[2][j], rb = s2[j];
+    Real sep = Num<Real>::abs(t) - ra - rb;
+    if (sep > margin) return 0;
+    if (sep > best + Real(1e-6) * (s1[0] + s1[1] + s1[2])) { best = sep; code = 3 + j; Real sg = t < 0 ? Real(-1) : Real(1); for (int k = 0; k < 3; ++k) bn[k] = sg * A2[j][k]; }
+  }
+  Real ebest = -Num<Real>::big; int ei = -1, ej = -1; Real en[3] = {0, 0, 0};
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) {
+    Real ax[3]; cross3(ax, A1[i], A2[j]);
+    Real l = Num<Real>::sqrt(dot3(ax, ax));
+    if (l < Real(1e-6)) continue;
+    for (int k = 0; k < 3; ++k) ax[k] /= l;
+    Real t = dot3(d, ax), ra = 0, rb = 0;
+    for (int k = 0; k < 3; ++k) { ra += s1[k] * Num<Real>::abs(dot3(A1[k], ax)); rb += s2[k] * Num<Real>::abs(dot3(A2[k], ax)); }
+    Real sep = Num<Real>::abs(t) - ra - rb;
+    if (sep > margin) return 0;
+    if (sep > ebest) { ebest = sep; ei = i; ej = j; Real sg = t < 0 ? Real(-1) : Real(1); for (int k = 0; k < 3; ++k) en[k] = sg * ax[k]; }
+  }
+  if (ei >= 0 && ebest > best + Real(1e-3) * Num<Real>::abs(best) + Real(1e-9)) {
+    Real c1[3] = {p1[0], p1[1], p1[2]}, c2[3] = {p2[0], p2[1], p2[2]};
+    for (int a = 0; a < 3; ++a) if (a != ei) { Real sg = dot3(A1[a], en) > 0 ? Real(1) : Real(-1); for (int k = 0; k < 3; ++k) c1[k] += sg * s1[a] * A1[a][k]; }
+    for (int a = 0; a < 3; ++a) if (a != ej) { Real sg = dot3(A2[a], en) > 0 ? Real(-1) : Real(1); for (int k = 0; k < 3; ++k) c2[k] += sg * s2[a] * A2[a][k]; }
+    const Real* u = A1[ei]; const Real* v = A2[ej];
+    Real w[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+    Real b = dot3(u, v), dd = dot3(u, w), e = dot3(v, w), den = 1 - b * b;
+    Real sa = (b * e - dd) / den, sb = (e - b * dd) / den;
+    sa = rmin(rmax(sa, -s1[ei]), s1[ei]); sb = rmin(rmax(sb, -s2[ej]), s2[ej]);
+    for (int k = 0; k < 3; ++k) { out[0][k] = Real(0.5) * (c1[k] + sa * u[k] + c2[k] + sb * v[k]); out[0][3 + k] = en[k]; }
+    out[0][6] = ebest;
+    return 1;
+  }
+  bool ref1 = code < 3; int ra = ref1 ? code : code - 3;
+  const Real *rp = ref1 ? p1 : p2, *ip = ref1 ? p2 : p1, *rs = ref1 ? s1 : s2, *is = ref1 ? s2 : s1;
+  Real(*RA)[3] = ref1 ? A1 : A2; Real(*IA)[3] = ref1 ? A2 : A1;
+  Real nref[3]; for (int k = 0; k < 3; ++k) nref[k] = ref1 ? bn[k] : -bn[k];
+  int ia = 0; Real mind = Num<Real>::big, isg = 1;
+  for (int a = 0; a < 3; ++a) { Real t = dot3(IA[a], nref); if (-Num<Real>::abs(t) < mind) { mind = -Num<Real>::abs(t); ia = a; isg = t > 0 ? Real(-1) : Real(1); } }
+  int iu = (ia + 1) % 3, iv = (ia + 2) % 3, ru = (ra + 1) % 3, rv = (ra + 2) % 3;
+  Real fc[3], rc[3];
+  for (int k = 0; k < 3; ++k) { fc[k] = ip[k] + isg * is[ia] * IA[ia][k]; rc[k] = rp[k] + rs[ra] * nref[k]; }
+  Real px[16], py[16];
+  for (int c = 0; c < 4; ++c) {
+    Real su = (c == 0 || c == 3) ? Real(1) : Real(-1), sv = (c < 2) ? Real(1) : Real(-1), r[3];
+    for (int k = 0; k < 3; ++k) r[k] = fc[k] + su * is[iu] * IA[iu][k] + sv * is[iv] * IA[iv][k] - rc[k];
+    px[c] = dot3(r, RA[ru]); py[c] = dot3(r, RA[rv]);
+  }
+  int n = 4;
+  n = clip_poly(px, py, n, Real(1), Real(0), rs[ru]); n = clip_poly(px, py, n, Real(-1), Real(0), rs[ru]);
+  n = clip_poly(px, py, n, Real(0), Real(1), rs[rv]); n = clip_poly(px, py, n, Real(0), Real(-1), rs[rv]);
+  if (n == 0) return 0;
+  Real ni[3]; for (int k = 0; k < 3; ++k) ni[k] = isg * IA[ia][k];
+  Real nn = dot3(ni, nref);
+  int cnt = 0;
+  for (int c = 0; c < n && cnt < STAGE_PTS; ++c) {
+    Real base[3], r[3];
+    for (int k = 0; k < 3; ++k) { base[k] = rc[k] + px[c] * RA[ru][k] + py[c] * RA[rv][k]; r[k] = fc[k] - base[k]; }
+    Real h = Num<Real>::abs(nn) > Real(1e-12) ? dot3(ni, r) / nn : Real(0);
+    if (h > margin) continue;
+    for (int k = 0; k < 3; ++k) { out[cnt][k] = base[k] + Real(0.5) * h * nref[k]; out[cnt][3 + k] = bn[k]; }
+    out[cnt][6] = h;
+    ++cnt;
+  }
+  return cnt;
+}
+
+template <typename Real, typename D>
+UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
+  if constexpr (!D::HAS_CONTACT) { s.ncon = 0; return; }
+  else {
+    WARP_FOR(p, m.npair) {
+      int g1 = m.pair_g1[p], g2 = m.pair_g2[p];
+      Real margin = m.pair_margin[p];
+      int n = 0;
+      const Real *x1 = s.geom_xpos[g1], *x2 = s.geom_xpos[g2];
+      if (m.geom_kind[g1] == GK_PLANE) {
+        const Real* pm = s.geom_xmat[g1];
+        Real h = (x2[0] - x1[0]) * pm[2] + (x2[1] - x1[1]) * pm[5] + (x2[2] - x1[2]) * pm[8];
+        if (h - m.geom_rbound[g2] <= margin) n = plane_box(x1, pm, x2, s.geom_xmat[g2], m.geom_size[g2], margin, s.u.stage[p]);
+      } else {
+        Real dd[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]}, r = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
+        if (dot3(dd, dd) <= r * r) n = box_box(x1, s.geom_xmat[g1], m.geom_size[g1], x2, s.geom_xmat[g2], m.geom_size[g2], margin, s.u.stage[p]);
+      }
+      int keep = 0;   // MuJoCo keeps a contact only when dist < margin
+      for (int c = 0; c < n; ++c) if (s.u.stage[p][c][6] < margin) { if (keep != c) for (int k = 0; k < 7; ++k) s.u.stage[p][keep][k] = s.u.stage[p][c][k]; ++keep; }
+      s.stage_n[p] = keep;
+    }
+    WARP_SYNC();
+    int total = 0;
+    for (int p = 0; p < m.npair; ++p) { int n = s.stage_n[p]; IF_LANE0 s.stage_off[p] = total; total += n; }
+    int ncon = total > D::MAXCON ? D::MAXCON : total;
+    IF_LANE0 { s.ncon = ncon; if (total > D::MAXCON) s.overflow |= 1; }
+    WARP_SYNC();
+    WARP_FOR(i, m.npair * STAGE_PTS) {
+      int p = i / STAGE_PTS, c = i % STAGE_PTS;
+      int o = s.stage_off[p] + c;
+      if (c < s.stage_n[p] && o < D::MAXCON) {
+        const Real* src = s.u.stage[p][c];
+        for (int k = 0; k < 3; ++k) { s.con_pos[o][k] = src[k]; s.con_frame[o][k] = src[3 + k]; }
+        s.con_dist[o] = src[6]; s.con_pair[o] = p;
+        make_frame(s.con_frame[o]);
+      }
+    }
+    WARP_SYNC();
+  }
+}
+
+// ---------------------------------------------------------------- constraints
+// translational jacobian column of dof d for a world point rigidly attached to `body`
+template <typename Real, typename D>
+UR3E_HD void jac_col(const DevModel<Real>& m, const Arena<Real, D>& s, int d, const Real* point, int body, Real* out) {
+  if ((m.body_dofmask[body] >> d) & 1u) {
+    const Real* ref = s.xpos[m.body_root[body]]; const Real* c = s.cdof[d];
+    Real off[3] = {point[0] - ref[0], point[1] - ref[1], point[2] - ref[2]}, t[3];
+    cross3(t, c, off);
+    out[0] = c[3] + t[0]; out[1] = c[4] + t[1]; out[2] = c[5] + t[2];
+  } else { out[0] = 0; out[1] = 0; out[2] = 0; }
+}
+
+template <typename Real> UR3E_HD Real impedance(const Real* si, Real pos, Real margin) {
+  const Real lo = Real(0.0001), hi = Real(0.9999);
+  Real s0 = rmin(rmax(si[0], lo), hi), s1 = rmin(rmax(si[1], lo), hi), s2 = rmax(si[2], Real(0)), s3 = rmin(rmax(si[3], lo), hi), s4 = rmax(si[4], Real(1));
+  if (s0 == s1 || s2 <= Num<Real>::minval) return Real(0.5) * (s0 + s1);
+  Real x = (pos - margin) / s2; if (x < 0) x = -x;
+  if (x >= 1 || x <= 0) return x >= 1 ? s1 : s0;
+  Real y;
+  if (s4 == 1) y = x;
+  else if (s4 == 2) y = x <= s3 ? x * x / s3 : 1 - (1 - x) * (1 - x) / (1 - s3);
+  else if (x <= s3) y = Num<Real>::pow(x, s4) / Num<Real>::pow(s3, s4 - 1);
+  else y = 1 - Num<Real>::pow(1 - x, s4) / Num<Real>::pow(1 - s3, s4 - 1);
+  return s0 + y * (s1 - s0);
+}
+
+template <typename Real> UR3E_HD void kb_params(const Real* solref, const Real* solimp, Real timestep, Real* K, Real* B) {
+  Real dmax = rmin(rmax(solimp[1], Real(0.0001)), Real(0.9999));
+  if (solref[0] > 0) {
+    Real tc = rmax(solref[0], 2 * timestep), dr = solref[1];
+    *K = 1 / rmax(Num<Real>::minval, dmax * dmax * tc * tc * dr * dr); *B = 2 / rmax(Num<Real>::minval, dmax * tc);
+  } else { *K = -solref[0] / rmax(Num<Real>::minval, dmax * dmax); *B = -solref[1] / rmax(Num<Real>::minval, dmax); }
+}
+
+template <typename Real, typename D>
+UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
+  const int nv = m.nv;
+  // row budget: equality, friction loss (static), limits (dynamic), contacts (3 rows each)
+  int ne = 0;
+  for (int e = 0; e < m.neq; ++e) ne += m.eq_kind[e] == EK_CONNECT ? 3 : 1;
+  const int nf = m.nfl;
+  int mlo = 0, mhi = 0;   // bit d: lower / upper limit of dof d is active (dist < margin)
+  WARP_FOR(d, nv) {
+    if (m.dof_limited[d]) {
+      Real q = s.qpos[m.dof_qadr[d]];
+      if ((q - m.dof_range[d][0]) < m.dof_margin[d]) mlo |= 1 << d;
+      if ((m.dof_range[d][1] - q) < m.dof_margin[d]) mhi |= 1 << d;
+    }
+  }
+  mlo = warp_or(mlo); mhi = warp_or(mhi);
+  const int nl = popcount32(mlo) + popcount32(mhi);
+  int base_c = ne + nf + nl;
+  int ncon = s.ncon;
+  if (base_c + 3 * ncon > D::MAXEFC) { ncon = (D::MAXEFC - base_c) / 3; if (ncon < 0) ncon = 0; IF_LANE0 { s.overflow |= 2; s.ncon = ncon; } }
+  int nefc = base_c + 3 * ncon; if (nefc > D::MAXEFC) nefc = D::MAXEFC;
+  IF_LANE0 { s.ne = ne; s.nf = nf; s.nl = nl; s.nefc = nefc; }
+  WARP_FOR(i, nefc * nv) (&s.u.efc_J[0][0])[i] = 0;
+  WARP_SYNC();
+  // equality rows; efc_aref temporarily holds pos, efc_R holds margin
+  {
+    int row = 0;
+    for (int e = 0; e < m.neq; ++e) {
+      if (m.eq_kind[e] == EK_CONNECT) {
+        int b1 = m.eq_o1[e], b2 = m.eq_o2[e];
+        Real a1[3], a2[3], v[3];
+        mat_vec3(v, s.xmat[b1], m.eq_data[e]); for (int k = 0; k < 3; ++k) a1[k] = s.xpos[b1][k] + v[k];
+        mat_vec3(v, s.xmat[b2], m.eq_data[e] + 3); for (int k = 0; k < 3; ++k) a2[k] = s.xpos[b2][k] + v[k];
+        WARP_FOR(d, nv) {
+          Real j1[3], j2[3]; jac_col(m, s, d, a1, b1, j1); jac_col(m, s, d, a2, b2, j2);
+          for (int r = 0; r < 3; ++r) s.u.efc_J[row + r][d] = j1[r] - j2[r];
+        }
+        WARP_FOR(r, 3) { s.efc_aref[row + r] = a1[r] - a2[r]; s.efc_R[row + r] = 0; s.efc_type[row + r] = ROW_EQ; s.efc_id[row + r] = e; s.efc_fl[row + r] = 0; }
+        row += 3;
+      } else {
+        IF_LANE0 {
+          int d1 = m.eq_o1[e], d2 = m.eq_o2[e];
+          const Real* c = m.eq_data[e];
+          Real p1 = s.qpos[m.dof_qadr[d1]] - m.qpos0[m.dof_qadr[d1]], pos, deriv = 0;
+          if (d2 >= 0) {
+            Real p2 = s.qpos[m.dof_qadr[d2]] - m.qpos0[m.dof_qadr[d2]];
+            pos = p1 - (c[0] + p2 * (c[1] + p2 * (c[2] + p2 * (c[3] + p2 * c[4]))));
+            deriv = c[1] + p2 * (2 * c[2] + p2 * (3 * c[3] + p2 * 4 * c[4]));
+            s.u.efc_J[row][d2] = -deriv;
+          } else pos = p1 - c[0];
+          s.u.efc_J[row][d1] = 1;
+          s.efc_aref[row] = pos; s.efc_R[row] = 0; s.efc_type[row] = ROW_EQ; s.efc_id[row] = e; s.efc_fl[row] = 0;
+        }
+        row += 1;
+      }
+    }
+  }
+  WARP_FOR(k, nf) {
+    int d = m.fl_dof[k], r = ne + k;
+    s.u.efc_J[r][d] = 1; s.efc_aref[r] = 0; s.efc_R[r] = 0; s.efc_type[r] = ROW_FRICTION; s.efc_id[r] = d; s.efc_fl[r] = m.dof_frictionloss[d];
+  }
+  WARP_FOR(i, 2 * nv) {
+    int d = i >> 1, k = i & 1;
+    int active = ((k == 0 ? mlo : mhi) >> d) & 1;
+    if (active) {
+      int below = (1 << d) - 1;
+      int r = ne + nf + popcount32(mlo & below) + popcount32(mhi & below) + (k == 1 ? ((mlo >> d) & 1) : 0);
+      if (r < D::MAXEFC) {
+        Real q = s.qpos[m.dof_qadr[d]];
+        s.u.efc_J[r][d] = k == 0 ? Real(1) : Real(-1);
+        s.efc_aref[r] = k == 0 ? q - m.dof_range[d][0] : m.dof_range[d][1] - q;
+        s.efc_R[r] = m.dof_margin[d]; s.efc_type[r] = ROW_LIMIT; s.efc_id[r] = d; s.efc_fl[r] = 0;
+      }
+    }
+  }
+  if constexpr (D::HAS_CONTACT) {
+    WARP_FOR(i, ncon * nv) {
+      int c = i / nv, d = i - c * nv, p = s.con_pair[c];
+      int b1 = m.geom_body[m.pair_g1[p]], b2 = m.geom_body[m.pair_g2[p]];
+      Real j1[3], j2[3]; jac_col(m, s, d, s.con_pos[c], b1, j1); jac_col(m, s, d, s.con_pos[c], b2, j2);
+      Real dj[3] = {j2[0] - j1[0], j2[1] - j1[1], j2[2] - j1[2]};
+      int r0 = base_c + 3 * c;
+      for (int r = 0; r < 3; ++r) s.u.efc_J[r0 + r][d] = dot3(s.con_frame[c] + 3 * r, dj);
+    }
+    WARP_FOR(i, 3 * ncon) {
+      int c = i / 3, r = i - 3 * c, row = base_c + i, p = s.con_pair[c];
+      s.efc_aref[row] = r == 0 ? s.con_dist[c] : Real(0); s.efc_R[row] = r == 0 ? m.pair_includemargin[p] : Real(0);
+      s.efc_type[row] = ROW_CON_N + r; s.efc_id[row] = c; s.efc_fl[row] = 0;
+      if (r == 0) s.con_row[c] = row;
+    }
+  }
+  WARP_SYNC();
+  // impedance, K/B, R, D, aref  (mj_makeImpedance + mj_referenceConstraint)
+  WARP_FOR(r, nefc) {
+    int t = s.efc_type[r], id = s.efc_id[r];
+    Real pos = s.efc_aref[r], margin = s.efc_R[r];
+    const Real *solref, *solimp; Real diag; bool fric = false;
+    if (t == ROW_EQ) { solref = m.eq_solref[id]; solimp = m.eq_solimp[id]; diag = m.eq_invw[id]; }
+    else if (t == ROW_FRICTION) { solref = m.dof_fl_solref[id]; solimp = m.dof_fl_solimp[id]; diag = m.dof_invw[id]; fric = true; }
+    else if (t == ROW_LIMIT) { solref = m.dof_lim_solref[id]; solimp = m.dof_lim_solimp[id]; diag = m.dof_invw[id]; }
+    else {
+      int p = s.con_pair[id]; solref = m.pair_solref[p]; solimp = m.pair_solimp[p]; diag = m.pair_invw[p];
+      if (t != ROW_CON_N) { fric = true; pos = 0; margin = 0; }
+    }
+    Real K, B; kb_params(solref, solimp, m.timestep, &K, &B);
+    Real imp = impedance(solimp, pos, margin);
+    Real R = rmax(Num<Real>::minval, (1 - imp) * diag / imp);
+    if (t >= ROW_CON_N) {
+      // elliptic cone: friction rows share the normal row's R scaled by 1/impratio (and by the friction ratio)
+      int p = s.con_pair[id];
+      Real impn = impedance(solimp, s.con_dist[id], m.pair_includemargin[p]);
+      Real Rn = rmax(Num<Real>::minval, (1 - impn) * diag / impn);
+      Real R1 = Rn / rmax(Num<Real>::minval, m.impratio);
+      if (t == ROW_CON_N) { R = Rn; s.con_mu[id] = m.pair_friction[p][0] * Num<Real>::sqrt(R1 / Rn); }
+      else if (t == ROW_CON_T1) R = R1;
+      else R = R1 * m.pair_friction[p][0] * m.pair_friction[p][0] / (m.pair_friction[p][1] * m.pair_friction[p][1]);
+    }
+    if (fric) K = 0;
+    Real vel = 0; for (int k = 0; k < nv; ++k) vel += s.u.efc_J[r][k] * s.qvel[k];
+    s.efc_R[r] = R; s.efc_D[r] = 1 / R;
+    s.efc_aref[r] = -B * vel - K * imp * (pos - margin);
+  }
+  WARP_SYNC();
+}
+
+// ---------------------------------------------------------------- dense SPD solve on the augmented matrix
+// Factors the leading n x n block of s.H (lower triangle) in place, with row n = rhs: after the call
+// H[n][0..n) = L^-1 rhs.  Then back-substitutes into x (shared memory, length n).
+template <typename Real, typename D>
+UR3E_HD void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
+  for (int j = 0; j < n; ++j) {
+    // column j: rows j..n (row n is the rhs)
+    WARP_FOR(i0, n + 1 - j) {
+      int i = j + i0;
+      Real t = s.H[i][j];
+      for (int k = 0; k < j; ++k) t -= s.H[i][k] * s.H[j][k];
+      s.H[i][j] = t;
+    }
+    WARP_SYNC();
+    Real djj = s.H[j][j];
+    djj = djj > Num<Real>::minval ? djj : Num<Real>::minval;
+    Real inv = 1 / Num<Real>::sqrt(djj);
+    WARP_SYNC();
+    WARP_FOR(i0, n + 1 - j) { int i = j + i0; s.H[i][j] = i == j ? djj * inv : s.H[i][j] * inv; }
+    WARP_SYNC();
+  }
+  WARP_FOR(i, n) x[i] = s.H[n][i];
+  WARP_SYNC();
+  for (int k = n - 1; k >= 0; --k) {
+    Real xk = x[k] / s.H[k][k];
+    WARP_SYNC();
+    WARP_FOR(i, k + 1) { if (i == k) x[i] = xk; else x[i] -= s.H[k][i] * xk; }
+    WARP_SYNC();
+  }
+}
+
+// ---------------------------------------------------------------- Newton solver on the primal problem
+// per-row cost derivative bookkeeping; cone contacts are processed by the lane that owns their normal row
+template <typename Real, typename D>
+UR3E_HD void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bool want_hess) {
+  WARP_FOR(r, s.nefc) {
+    int t = s.efc_type[r];
+    Real Dr = s.efc_D[r], x = s.efc_jar[r];
+    if (t == ROW_EQ) { s.efc_force[r] = -Dr * x; s.efc_Dact[r] = Dr; }
+    else if (t == ROW_FRICTION) {
+      Real f = s.efc_fl[r], rf = s.efc_R[r] * f;
+      if (x <= -rf) { s.efc_force[r] = f; s.efc_Dact[r] = 0; }
+      else if (x >= rf) { s.efc_force[r] = -f; s.efc_Dact[r] = 0; }
+      else { s.efc_force[r] = -Dr * x; s.efc_Dact[r] = Dr; }
+    } else if (t == ROW_LIMIT) {
+      if (x < 0) { s.efc_force[r] = -Dr * x; s.efc_Dact[r] = Dr; } else { s.efc_force[r] = 0; s.efc_Dact[r] = 0; }
+    } else if (t == ROW_CON_N) {
+      int c = s.efc_id[r], p = s.con_pair[c];
+      Real mu = s.con_mu[c], f1 = m.pair_friction[p][0], f2 = m.pair_friction[p][1];
+      Real U0 = x * mu, U1 = s.efc_jar[r + 1] * f1, U2 = s.efc_jar[r + 2] * f2;
+      Real T = Num<Real>::sqrt(U1 * U1 + U2 * U2), N = U0;
+      Real* Hc = s.con_H[c];
+      if (N >= mu * T || (T <= 0 && N >= 0)) {
+        for (int j = 0; j < 3; ++j) { s.efc_force[r + j] = 0; s.efc_Dact[r + j] = 0; }
+        Hc[0] = -1;   // marker: no cone hessian
+      } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+        for (int j = 0; j < 3; ++j) { s.efc_force[r + j] = -s.efc_D[r + j] * s.efc_jar[r + j]; s.efc_Dact[r + j] = s.efc_D[r + j]; }
+        Hc[0] = -1;
+      } else {
+        Real Dm = Dr / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+        Real f0 = -Dm * NmT * mu;
+        s.efc_force[r] = f0; s.efc_force[r + 1] = -f0 / T * U1 * f1; s.efc_force[r + 2] = -f0 / T * U2 * f2;
+        for (int j = 0; j < 3; ++j) s.efc_Dact[r + j] = 0;
+        if (want_hess) {
+          Real u1 = U1 / T, u2 = U2 / T, a = Dm * mu * mu, b = -Dm * mu * NmT / T;
+          // symmetric 3x3 wrt jar: [00, 01, 02, 11, 12, 22]
+          Hc[0] = Dm * mu * mu; Hc[1] = -Dm * mu * u1 * mu * f1; Hc[2] = -Dm * mu * u2 * mu * f2;
+          Hc[3] = (a * u1 * u1 + b * (1 - u1 * u1)) * f1 * f1; Hc[4] = (a * u1 * u2 - b * u1 * u2) * f1 * f2; Hc[5] = (a * u2 * u2 + b * (1 - u2 * u2)) * f2 * f2;
+        } else Hc[0] = 0;
+      }
+    }
+  }
+  WARP_SYNC();
+}
+
+// derivative / curvature of the cost along qacc + alpha * search (constraint part)
+template <typename Real, typename D>
+UR3E_HD void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real alpha, Real g1, Real g2, Real* dphi, Real* ddphi) {
+  Real p1 = 0, p2 = 0;
+  WARP_FOR(r, s.nefc) {
+    int t = s.efc_type[r];
+    Real Dr = s.efc_D[r], v = s.efc_jv[r], x = s.efc_jar[r] + alpha * v;
+    if (t == ROW_EQ) { p1 += Dr * x * v; p2 += Dr * v * v; }
+    else if (t == ROW_FRICTION) {
+      Real f = s.efc_fl[r], rf = s.efc_R[r] * f;
+      if (x <= -rf) p1 -= f * v; else if (x >= rf) p1 += f * v; else { p1 += Dr * x * v; p2 += Dr * v * v; }
+    } else if (t == ROW_LIMIT) { if (x < 0) { p1 += Dr * x * v; p2 += Dr * v * v; } }
+    else if (t == ROW_CON_N) {
+      int c = s.efc_id[r], p = s.con_pair[c];
+      Real mu = s.con_mu[c], f1 = m.pair_friction[p][0], f2 = m.pair_friction[p][1];
+      Real x1 = s.efc_jar[r + 1] + alpha * s.efc_jv[r + 1], x2 = s.efc_jar[r + 2] + alpha * s.efc_jv[r + 2];
+      Real U0 = x * mu, U1 = x1 * f1, U2 = x2 * f2, V0 = v * mu, V1 = s.efc_jv[r + 1] * f1, V2 = s.efc_jv[r + 2] * f2;
+      Real T = Num<Real>::sqrt(U1 * U1 + U2 * U2), N = U0;
+      if (N >= mu * T || (T <= 0 && N >= 0)) { }
+      else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+        p1 += Dr * x * v + s.efc_D[r + 1] * x1 * s.efc_jv[r + 1] + s.efc_D[r + 2] * x2 * s.efc_jv[r + 2];
+        p2 += Dr * v * v + s.efc_D[r + 1] * s.efc_jv[r + 1] * s.efc_jv[r + 1] + s.efc_D[r + 2] * s.efc_jv[r + 2] * s.efc_jv[r + 2];
+      } else {
+        Real Dm = Dr / (mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+        Real UV = U1 * V1 + U2 * V2, VV = V1 * V1 + V2 * V2;
+        Real T1 = UV / T, T2 = VV / T - UV * UV / (T * T * T), dN = V0 - mu * T1;
+        p1 += Dm * NmT * dN; p2 += Dm * (dN * dN - NmT * mu * T2);
+      }
+    }
+  }
+  *dphi = g1 + alpha * g2 + warp_sum(p1);
+  *ddphi = g2 + warp_sum(p2);
+}
+
+template <typename Real> struct SolverOpts { int max_iter; int max_ls; Real tol; Real ls_tol; };
+
+template <typename Real, typename D>
+UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
+  const int nv = m.nv, nefc = s.nefc;
+  if (nefc == 0) {
+    // unconstrained: qacc = M^-1 qfrc_smooth
+    WARP_FOR(i, nv * (nv + 1)) { int r = i / nv, c = i - r * nv; s.H[r][c] = r < nv ? s.M[r][c] : s.qfrc_smooth[c]; }
+    WARP_FOR(d, nv) s.qfrc_constraint[d] = 0;
+    WARP_SYNC();
+    chol_solve_aug(s, nv, s.qacc);
+    IF_LANE0 s.solver_iter = 0;
+    return;
+  }
+  const Real scale = Real(1) / (m.meaninertia * Real(nv > 1 ? nv : 1));
+  WARP_FOR(d, nv) s.qacc[d] = s.qacc_ws[d];
+  WARP_SYNC();
+  WARP_FOR(i, nv + nefc) {
+    if (i < nv) { Real v = 0; for (int k = 0; k < nv; ++k) v += s.M[i][k] * s.qacc[k]; s.Ma[i] = v; }
+    else { int r = i - nv; Real v = -s.efc_aref[r]; for (int k = 0; k < nv; ++k) v += s.u.efc_J[r][k] * s.qacc[k]; s.efc_jar[r] = v; }
+  }
+  WARP_SYNC();
+  int iter = 0;
+  for (; iter < opt.max_iter; ++iter) {
+    constraint_update(m, s, true);
+    Real gg = 0;
+    WARP_FOR(d, nv) {
+      Real g = s.Ma[d] - s.qfrc_smooth[d];
+      for (int r = 0; r < nefc; ++r) g -= s.u.efc_J[r][d] * s.efc_force[r];
+      s.grad[d] = g; gg += g * g;
+    }
+    gg = warp_sum(gg);
+    if (scale * Num<Real>::sqrt(gg) < opt.tol) break;
+    // H = M + J^T diag(Dact) J + cone blocks ; augmented row = -grad
+    WARP_FOR(e, (nv + 1) * (nv + 2) / 2) {
+      int ab = m.tri_ab[e], a = ab >> 8, b = ab & 255;   // (a, b), b <= a, over the (nv+1) x (nv+1) lower triangle
+      if (a == nv) { if (b < nv) s.H[nv][b] = -s.grad[b]; }
+      else {
+        Real h = s.M[a][b];
+        for (int r = 0; r < nefc; ++r) { Real da = s.efc_Dact[r]; if (da != 0) h += da * s.u.efc_J[r][a] * s.u.efc_J[r][b]; }
+        if constexpr (D::HAS_CONTACT) {
+          for (int c = 0; c < s.ncon; ++c) {
+            const Real* Hc = s.con_H[c];
+            if (Hc[0] > 0) {
+              int r = s.con_row[c];
+              Real a0 = s.u.efc_J[r][a], a1 = s.u.efc_J[r + 1][a], a2 = s.u.efc_J[r + 2][a];
+              Real b0 = s.u.efc_J[r][b], b1 = s.u.efc_J[r + 1][b], b2 = s.u.efc_J[r + 2][b];
+              h += Hc[0] * a0 * b0 + Hc[1] * (a0 * b1 + a1 * b0) + Hc[2] * (a0 * b2 + a2 * b0) + Hc[3] * a1 * b1 + Hc[4] * (a1 * b2 + a2 * b1) + Hc[5] * a2 * b2;
+            }
+          }
+        }
+        s.H[a][b] = h;
+      }
+    }
+    WARP_SYNC();
+    chol_solve_aug(s, nv, s.search);
+    // Mv, jv, and the quadratic (Gauss) part of the line cost
+    WARP_FOR(i, nv + nefc) {
+      if (i < nv) { Real v = 0; for (int k = 0; k < nv; ++k) v += s.M[i][k] * s.search[k]; s.Mv[i] = v; }
+      else { int r = i - nv; Real v = 0; for (int k = 0; k < nv; ++k) v += s.u.efc_J[r][k] * s.search[k]; s.efc_jv[r] = v; }
+    }
+    WARP_SYNC();
+    Real g1 = 0, g2 = 0, sn = 0;
+    WARP_FOR(d, nv) { g1 += s.search[d] * (s.Ma[d] - s.qfrc_smooth[d]); g2 += s.search[d] * s.Mv[d]; sn += s.search[d] * s.search[d]; }
+    g1 = warp_sum(g1); g2 = warp_sum(g2); sn = warp_sum(sn);
+    // exact line search: safeguarded Newton on phi'(alpha)
+    Real p1, p2, lo = 0, hi = -1, alpha;
+    line_eval(m, s, Real(0), g1, g2, &p1, &p2);
+    if (!(p1 < 0)) break;
+    const Real p10 = -p1;
+    alpha = -p1 / p2;
+    for (int ls = 0; ls < opt.max_ls; ++ls) {
+      line_eval(m, s, alpha, g1, g2, &p1, &p2);
+      if (Num<Real>::abs(p1) < opt.ls_tol * p10) break;
+      if (p1 < 0) lo = alpha; else hi = alpha;
+      Real na = alpha - p1 / p2;
+      if (hi < 0) { if (!(na > lo)) na = 2 * alpha; }
+      else if (!(na > lo && na < hi)) na = Real(0.5) * (lo + hi);
+      if (na == alpha) break;
+      alpha = na;
+    }
+    WARP_FOR(i, nv + nefc) {
+      if (i < nv) { s.qacc[i] += alpha * s.search[i]; s.Ma[i] += alpha * s.Mv[i]; }
+      else s.efc_jar[i - nv] += alpha * s.efc_jv[i - nv];
+    }
+    WARP_SYNC();
+    if (scale * alpha * Num<Real>::sqrt(sn) * m.meaninertia < opt.tol * Real(1e-3)) { ++iter; break; }
+  }
+  constraint_update(m, s, false);
+  WARP_FOR(d, nv) { Real v = 0; for (int r = 0; r < nefc; ++r) v += s.u.efc_J[r][d] * s.efc_force[r]; s.qfrc_constraint[d] = v; }
+  IF_LANE0 s.solver_iter = iter;
+  WARP_SYNC();
+}
+
+// ---------------------------------------------------------------- one mj_step
+template <typename Real, typename D>
+UR3E_HD void forward(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, bool with_solver) {
+  kinematics(m, s);
+  dynamics(m, s);
+  collision(m, s);
+  if (with_solver) { make_constraint(m, s); solve(m, s, opt); }
+}
+
+template <typename Real, typename D>
+UR3E_HD void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
+  WARP_FOR(i, m.nq) s.qpos[i] = m.qpos0[i];
+  WARP_FOR(i, m.nv) { s.qvel[i] = 0; s.qacc_ws[i] = 0; s.qacc[i] = 0; }
+  WARP_FOR(i, m.nu) s.ctrl[i] = 0;
+  WARP_SYNC();
+}
+
+template <typename Real> UR3E_HD int is_bad(Real x) { return !(x == x) || x > Real(1e10) || x < Real(-1e10); }
+
+template <typename Real, typename D>
+UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
+  const int nv = m.nv; const Real h = m.timestep;
+  Real* qa = s.qacc;
+  if (m.has_damping) {
+    // (M + h diag(damping)) a = qfrc_smooth + qfrc_constraint   
+    WARP_FOR(i, nv * (nv + 1)) {
+      int r = i / nv, c = i - r * nv;
+      s.H[r][c] = r < nv ? s.M[r][c] + (r == c ? h * m.dof_damping[r] : Real(0)) : s.qfrc_smooth[c] + s.qfrc_constraint[c];
+    }
+    WARP_SYNC();
+    chol_solve_aug(s, nv, s.search);
+    qa = s.search;
+  }
+  WARP_FOR(d, nv) s.qvel[d] += h * qa[d];
+  WARP_SYNC();
+  WARP_FOR(d, nv) {
+    int fk = m.dof_free_k[d], q = m.dof_qadr[d];
+    if (fk < 0 || fk < 3) s.qpos[q] += h * s.qvel[d];
+    else if (fk == 3) {
+      Real w[3] = {s.qvel[d], s.qvel[d + 1], s.qvel[d + 2]};
+      Real n = Num<Real>::sqrt(dot3(w, w)), ang = h * n;
+      Real qr[4] = {1, 0, 0, 0};
+      if (n >= Num<Real>::minval && ang != 0) { Real sn = Num<Real>::sin(ang * Real(0.5)) / n; qr[0] = Num<Real>::cos(ang * Real(0.5)); qr[1] = w[0] * sn; qr[2] = w[1] * sn; qr[3] = w[2] * sn; }
+      Real qq[4] = {s.qpos[q], s.qpos[q + 1], s.qpos[q + 2], s.qpos[q + 3]}, out[4];
+      quat_normalize(qq); quat_mul(out, qq, qr);
+      for (int k = 0; k < 4; ++k) s.qpos[q + k] = out[k];
+    }
+  }
+  WARP_SYNC();
+}
+
+// returns a warning mask: 1 bad qpos, 2 bad qvel, 4 bad qacc (mj_checkPos/Vel/Acc + autoreset)
+template <typename Real, typename D>
+UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
+  int w = 0;
+  WARP_FOR(i, m.nq + m.nv) w |= i < m.nq ? is_bad(s.qpos[i]) : 2 * is_bad(s.qvel[i - m.nq]);
+  w = warp_or(w);
+  if (w) reset_data(m, s);
+  forward(m, s, opt, true);
+  int wa = 0;
+  WARP_FOR(i, m.nv) wa |= 4 * is_bad(s.qacc[i]);
+  wa = warp_or(wa);
+  if (wa) { reset_data(m, s); forward(m, s, opt, true); w |= wa; }
+  WARP_FOR(d, m.nv) s.qacc_ws[d] = s.qacc[d];
+  WARP_SYNC();
+  euler(m, s);
+  return w;
+}
+
+}  // namespace ur3e
