@@ -24,15 +24,15 @@ static int run(const HostModel& h, const double* qpos, const double* qvel, const
   DevModel<Real> m = compile_model<Real>(h);
   auto s = std::make_unique<Arena<Real, D>>();
   std::memset(s.get(), 0, sizeof(Arena<Real, D>));
-  for (int i = 0; i < h.nq; ++i) s->qpos[i] = (Real)qpos[i];
-  for (int i = 0; i < h.nv; ++i) { s->qvel[i] = (Real)qvel[i]; s->qacc_ws[i] = (Real)ws[i]; }
+  for (int i = 0; i < h.nq; ++i) s->st.qpos[i] = (Real)qpos[i];
+  for (int i = 0; i < h.nv; ++i) { s->st.qvel[i] = (Real)qvel[i]; s->st.qacc_ws[i] = (Real)ws[i]; }
   for (int i = 0; i < h.nu; ++i) s->ctrl[i] = (Real)ctrl[i];
   SolverOpts<Real> opt{max_iter, 50, (Real)tol, (Real)(sizeof(Real) == 8 ? 1e-14 : 1e-6)};
   int w = 0;
   if (nsteps == 0) forward(m, *s, opt, true);
   for (int k = 0; k < nsteps; ++k) w |= substep(m, *s, opt);
-  for (int i = 0; i < h.nq; ++i) oq[i] = s->qpos[i];
-  for (int i = 0; i < h.nv; ++i) { ov[i] = s->qvel[i]; oa[i] = nsteps == 0 ? s->qacc[i] : s->qacc_ws[i]; obias[i] = s->qfrc_bias[i]; ofc[i] = s->qfrc_constraint[i]; }
+  for (int i = 0; i < h.nq; ++i) oq[i] = s->st.qpos[i];
+  for (int i = 0; i < h.nv; ++i) { ov[i] = s->st.qvel[i]; oa[i] = nsteps == 0 ? s->qacc[i] : s->st.qacc_ws[i]; obias[i] = s->qfrc_bias[i]; ofc[i] = s->qfrc_constraint[i]; }
   for (int i = 0; i < h.nv; ++i) for (int j = 0; j < h.nv; ++j) oM[i * h.nv + j] = s->M[i][j];
   info[0] = s->ncon; info[1] = s->nefc; info[2] = s->solver_iter; info[3] = w; info[4] = s->overflow; info[5] = (int)sizeof(Arena<Real, D>);
   return 0;

@@ -1,0 +1,178 @@
+"""GPU parity: the CUDA path (through the C ABI) against the float64 oracle on identical states and actions.
+
+Tolerances (BASELINE.json north_star): float64 build <= 1e-9 relative per step on contact-free trajectories,
+<= 1e-4 relative per step (re-seeded from the oracle state) on contact-rich ones; float32 drift bounds stated per test.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import envs as OE
+from oracle import oracle as O
+import ur3e_b200._lib as lib
+from ur3e_b200.batch import SimBatch, env_config
+from ur3e_b200.model import Model
+
+
+def rel(a, b, floor=1e-3):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / (np.abs(b) + floor)))
+
+
+def make(assets, xml, n, dtype, **cfg):
+    m = Model(assets + "/" + xml)
+    c = env_config(**cfg)
+    return SimBatch(m, c, n, 0, dtype)
+
+
+def test_raw_move_j_f64(assets):
+    """config 1: ur3e_raw.xml, pd_joint_ctrl on a joint-space trajectory, no re-seeding, 1e-9 relative per step."""
+    xml = assets + "/ur3e_raw.xml"
+    loop = OE.OracleCtrlLoop(xml, "pd_joint", OE.GAINS_J)
+    b = make(assets, "ur3e_raw.xml", 2, torch.float64, ctrl_mode=lib.CTRL_PD_JOINT, obs_kind=lib.OBS_STATE, obs_dim=12, act_dim=6, gains=OE.GAINS_J)
+    b.reset()
+    loop.set_state(np.zeros(6), np.zeros(6))
+    rng = np.random.default_rng(42)
+    way = np.cumsum(rng.uniform(-0.02, 0.02, (40, 6)), axis=0)
+    worst = 0.0
+    for k in range(4000):
+        tgt = way[k // 100]
+        qp, qv = loop.step(tgt)
+        a = torch.tensor(np.tile(tgt, (2, 1)), dtype=torch.float64, device="cuda")
+        obs, *_ = b.step(a)
+        o = obs[0].cpu().numpy()
+        worst = max(worst, rel(o[:6], qp), rel(o[6:], qv))
+    assert worst < 1e-9, worst
+    assert torch.equal(obs[0], obs[1])
+
+
+def test_gripper_task_space_f64(assets):
+    """config 2 semantics: ur3e_2f85.xml, pid_task_ctrl every mj_step, contact-free, 1e-9 relative per step (no re-seeding)."""
+    xml = assets + "/ur3e_2f85.xml"
+    loop = OE.OracleCtrlLoop(xml, "pid_task", OE.GAINS_TASK)
+    b = make(assets, "ur3e_2f85.xml", 1, torch.float64, ctrl_mode=lib.CTRL_PID_TASK, obs_kind=lib.OBS_STATE, obs_dim=28, act_dim=7, gains=OE.GAINS_TASK, reset_key=1)
+    b.reset()
+    qp, qv = loop.m.key("down"); loop.set_state(qp, qv)
+    loop.d.forward()
+    tcp0 = loop.d.site_xpos.reshape(-1, 3)[loop.tcp].copy()
+    worst = 0.0
+    for k in range(1500):
+        tgt = np.hstack([tcp0 + [0.05, -0.03, 0.04], OE.TOOL_ROTVEC, 0.5 if k > 700 else 0.0])
+        qp, qv = loop.step(tgt)
+        obs, *_ = b.step(torch.tensor(tgt[None], dtype=torch.float64, device="cuda"))
+        o = obs[0].cpu().numpy()
+        worst = max(worst, rel(o[:14], qp), rel(o[14:], qv))
+    assert worst < 1e-9, worst
+
+
+def _random_states(m, rng, n, lift=False):
+    qp0, _ = m.key("down")
+    qp = np.tile(qp0, (n, 1)); qv = rng.uniform(-0.5, 0.5, (n, m.nv))
+    qp[:, :6] += rng.uniform(-0.3, 0.3, (n, 6))
+    qp[:, 6] = qp[:, 10] = rng.uniform(0, 0.6, n)
+    qp[:, 16] -= rng.uniform(0, 0.002, n)  # mug pressed into the table: contacts active
+    return qp, qv
+
+
+def test_main_forward_internals_f64(assets):
+    """mj_forward quantities (M, qfrc_bias, qacc, ncon, nefc) on random main.xml states with mug-table contacts."""
+    m = O.Model(assets + "/main.xml"); d = O.Data(m)
+    rng = np.random.default_rng(3)
+    n = 8
+    qp, qv = _random_states(m, rng, n)
+    b = make(assets, "main.xml", n, torch.float64, ctrl_mode=lib.CTRL_RAW, obs_kind=lib.OBS_STATE, obs_dim=32 if False else 41 - 9, act_dim=7) if False else None
+    b = make(assets, "main.xml", n, torch.float64, ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2, reset_key=1, term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500)
+    b.reset()
+    b.set_state(torch.tensor(qp, device="cuda"), torch.tensor(qv, device="cuda"))
+    for e in range(n):
+        d.reset(); d.set_state(qp[e], qv[e]); d.forward()
+        g = b.debug_forward(e)
+        assert g["ncon"] == d.ncon and g["nefc"] == d.nefc
+        assert rel(g["M"], d.fullM(), 1e-6) < 1e-9
+        assert rel(g["qfrc_bias"], d.qfrc_bias) < 1e-9
+        assert rel(g["qacc"], d.qacc, 1e-1) < 1e-6
+        jp, jr = d.jac_site(m.id("site", "tcp"))
+        assert rel(g["J_arm"], np.vstack([jp[:, :6], jr[:, :6]]), 1e-3) < 1e-9
+
+
+@pytest.mark.parametrize("kind", ["v2", "v0", "indirect"])
+def test_env_step_reseeded_f64(assets, kind):
+    """Env.step parity (obs, reward, done) with per-step re-seeding from the oracle state: <= 1e-4 relative per step."""
+    xml = assets + "/main.xml"
+    env = OE.OracleEnv(xml, kind)
+    cfgs = dict(
+        v2=dict(obs_kind=lib.OBS_V2, obs_dim=24, frame_skip=2, term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500, gains=OE.GAINS_MUG),
+        v0=dict(obs_kind=lib.OBS_V0, obs_dim=13, frame_skip=2, term_kind=lib.TERM_V0, reward_kind=lib.REW_V0, max_steps=500, gains=OE.GAINS_V0),
+        indirect=dict(obs_kind=lib.OBS_V2, obs_dim=24, frame_skip=1, term_kind=lib.TERM_NONE, reward_kind=lib.REW_MINUS1, max_steps=2500, gains=OE.GAINS_MUG))
+    b = make(assets, "main.xml", 1, torch.float64, ctrl_mode=lib.CTRL_PID_TASK_ENV, act_dim=4, reset_key=1, **cfgs[kind])
+    b.reset()
+    o0 = env.reset()
+    assert rel(b.obs[0].cpu().numpy(), o0) < 1e-9
+    rng = np.random.default_rng(7)
+    mug = o0[3:6].copy()
+    worst = 0.0
+    for k in range(300):
+        # scripted approach + grasp so that pad-mug contacts occur
+        tgt = mug + [0, 0, 0.02 + max(0.0, 0.1 - 0.001 * k)]
+        a = np.hstack([tgt + rng.normal(0, 0.002, 3), 1.0 if k > 150 else 0.0])
+        # re-seed the GPU state from the oracle's (qpos, qvel, warmstart) and replay its stale cache by stepping from the same state
+        qp, qv, ws = env.d.qpos.copy(), env.d.qvel.copy(), env.d.qacc_warmstart.copy()
+        if k % 25 == 0:
+            env.set_state(qp, qv); env.t = k
+            b.set_state(torch.tensor(qp[None], device="cuda"), torch.tensor(qv[None], device="cuda"))
+        o, r, te, tr = env.step(a)
+        obs, rew, term, trunc = b.step(torch.tensor(a[None], dtype=torch.float64, device="cuda"))
+        worst = max(worst, rel(obs[0].cpu().numpy(), o), rel(rew[0].item(), r, 1.0))
+        assert bool(term[0].item()) == te and bool(trunc[0].item()) == tr, (k, term, te, trunc, tr)
+        if te or tr:
+            break
+    assert worst < 1e-4, worst
+
+
+def test_f32_drift_main(assets):
+    """float32 production build vs the float64 build on the v2 env: stated drift bound over 200 env-steps of a resting scene
+    (obs abs error <= 2e-3; the scripted motion is slow so the chaos of contact switching is not excited)."""
+    cfg = dict(ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2, reset_key=1,
+               term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500)
+    b32 = make(assets, "main.xml", 4, torch.float32, **cfg); b64 = make(assets, "main.xml", 4, torch.float64, **cfg)
+    o32 = b32.reset().clone(); o64 = b64.reset().clone()
+    assert torch.allclose(o32.double(), o64, atol=1e-5)
+    a = o64[:, 0:3].clone(); a[:, 2] += 0.02
+    a = torch.cat([a, torch.zeros(4, 1, dtype=torch.float64, device="cuda")], 1)
+    for k in range(200):
+        o64, *_ = b64.step(a); o32, *_ = b32.step(a.float())
+    assert torch.isfinite(o32).all()
+    assert (o32.double() - o64).abs().max().item() < 2e-3
+
+
+def test_auto_reset_and_stats(assets):
+    """In-kernel auto-reset: truncation after max_steps resets t, returns the reset obs and keeps the terminal obs; counters add up."""
+    n = 64
+    b = make(assets, "main.xml", n, torch.float32, ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2,
+             reset_key=1, term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=5, auto_reset=1, reset_noise=lib.NOISE_HIGH)
+    o0 = b.reset(seed=123).clone()
+    assert o0[:, 3].std() > 0 and o0[:, 4].std() > 0            # mug x,y noise differs per env
+    assert (o0[:, 3] >= 0.29799994 - 1e-6).all() and (o0[:, 3] <= 0.31799994 + 1e-6).all()
+    a = torch.cat([o0[:, 0:3], torch.zeros(n, 1, device="cuda")], 1).contiguous()
+    ndone = 0
+    for k in range(10):
+        obs, rew, term, trunc = b.step(a)
+        ndone += int((term | trunc).sum().item())
+        if k == 4:
+            assert trunc.all()
+    st = b.stats_dict()
+    assert st["episodes"] == ndone and st["substeps"] == n * 10 * 2
+    assert st["length_sum"] == 5 * ndone
+
+
+def test_host_entry_point(assets):
+    n = 32
+    b = make(assets, "main.xml", n, torch.float32, ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2,
+             reset_key=1, term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500)
+    o0 = b.reset().cpu().numpy()
+    a = np.ascontiguousarray(np.hstack([o0[:, :3], np.zeros((n, 1))]).astype(np.float32))
+    obs = np.zeros((n, 24), np.float32); rew = np.zeros(n, np.float32); te = np.zeros(n, np.uint8); tr = np.zeros(n, np.uint8)
+    b.step_host(a, obs, rew, te, tr)
+    assert np.isfinite(obs).all() and np.abs(obs[:, :3] - o0[:, :3]).max() < 1e-2

@@ -1,0 +1,45 @@
+// Type-erased batch interface + per-(dtype, size class) factories (each factory lives in its own
+// translation unit so the six kernel instantiations compile in parallel).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <memory>
+#include <string>
+
+#include "../../include/ur3e_b200.h"
+#include "host_model.h"
+
+namespace ur3e {
+
+inline thread_local std::string g_err;
+inline int set_err(const std::string& e, int code = -1) { g_err = e; return code; }
+#define CUDA_OK(expr)                                                                                       \
+  do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return ::ur3e::set_err(std::string(#expr) + ": " + cudaGetErrorString(e_), -2); } while (0)
+
+constexpr int WPB = 4;  // warps (environments) per block
+
+struct BatchBase {
+  virtual ~BatchBase() {}
+  virtual int reset(const uint8_t* mask, uint64_t seed, void* obs, cudaStream_t s) = 0;
+  virtual int step(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc, void* fobs, cudaStream_t s) = 0;
+  virtual int step_host(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc) = 0;
+  virtual int get_state(void* qpos, void* qvel, void* ws, cudaStream_t s) = 0;
+  virtual int set_state(const void* qpos, const void* qvel, const void* ws, cudaStream_t s) = 0;
+  virtual int stats(double* out, int reset, cudaStream_t s) = 0;
+  virtual int debug(long long env, double* M, double* bias, double* qacc, double* fc, int32_t* info, double* con, double* cache) = 0;
+  int64_t launches = 0;
+  int arena_bytes = 0, blocks_per_sm = 0, regs = 0, device = 0;
+  long long n = 0;
+};
+
+
+// returns nullptr (and sets the error) on failure
+std::unique_ptr<BatchBase> make_batch_f32_raw(const HostModel&, const ur3e_env_config&, long long n, int device);
+std::unique_ptr<BatchBase> make_batch_f64_raw(const HostModel&, const ur3e_env_config&, long long n, int device);
+std::unique_ptr<BatchBase> make_batch_f32_grip(const HostModel&, const ur3e_env_config&, long long n, int device);
+std::unique_ptr<BatchBase> make_batch_f64_grip(const HostModel&, const ur3e_env_config&, long long n, int device);
+std::unique_ptr<BatchBase> make_batch_f32_main(const HostModel&, const ur3e_env_config&, long long n, int device);
+std::unique_ptr<BatchBase> make_batch_f64_main(const HostModel&, const ur3e_env_config&, long long n, int device);
+
+}  // namespace ur3e

@@ -1,0 +1,287 @@
+// The sm_100a kernels that run the fused environment step + the typed batch object behind the C ABI.
+// One warp per environment, WPB warps per block, one shared-memory Arena per warp (engine.cuh / env.cuh).
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "batch_base.h"
+#include "compile_model.h"
+#include "env.cuh"
+
+namespace ur3e {
+enum Op { OP_STEP = 0, OP_RESET = 1, OP_SET_STATE = 2, OP_DEBUG = 3 };
+
+template <typename Real, typename D>
+struct KArgs {
+  const DevModel<Real>* m;
+  EnvCfg<Real> c;
+  SolverOpts<Real> opt;
+  EnvState<Real, D>* st;
+  long long n;
+  int op;
+  const Real* act; Real* obs; Real* rew; uint8_t* term; uint8_t* trunc; Real* final_obs;
+  const uint8_t* mask;
+  unsigned long long seed, env_base;
+  const Real* qpos_in; const Real* qvel_in; const Real* ws_in;
+  long long dbg_env; double* dbg;
+};
+
+template <typename Real, typename D> __host__ __device__ constexpr size_t arena_stride() { return (sizeof(Arena<Real, D>) + 15) / 16 * 16; }
+constexpr int DBG_DOUBLES = MAXV * MAXV + 3 * MAXV + 8 + 4 * MAXCON + CACHE_SIZE;
+
+template <typename Real, typename D>
+__global__ void __launch_bounds__(WPB * 32) env_kernel(const KArgs<Real, D> a) {
+  extern __shared__ int4 smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  long long e = (long long)blockIdx.x * WPB + warp;
+  if (a.op == OP_DEBUG) { if (blockIdx.x != 0 || warp != 0) return; e = a.dbg_env; }
+  if (e >= a.n) return;
+  Arena<Real, D>& s = *reinterpret_cast<Arena<Real, D>*>(reinterpret_cast<unsigned char*>(smem_raw) + warp * arena_stride<Real, D>());
+  const DevModel<Real>& m = *a.m;
+  const EnvCfg<Real>& c = a.c;
+  constexpr int NW = sizeof(EnvState<Real, D>) / 16;
+  int4* gst = reinterpret_cast<int4*>(a.st + e);
+  int4* sst = reinterpret_cast<int4*>(&s.st);
+  if (a.op == OP_RESET && a.mask && !a.mask[e]) return;
+  WARP_FOR(i, NW) sst[i] = gst[i];
+  IF_LANE0 { s.overflow = 0; s.ncon = 0; s.nefc = 0; s.solver_iter = 0; }
+  WARP_SYNC();
+  const int od = c.obs_dim;
+  if (a.op == OP_STEP) {
+    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim);
+    const int done = r.terminated | r.truncated;
+    if (done && a.final_obs) { WARP_FOR(i, od) a.final_obs[e * od + i] = s.obs[i]; }
+    if (done && c.auto_reset) {
+      env_reset(m, c, s, a.opt, a.seed, a.env_base + (unsigned long long)e);
+      ContactFlags cf = contact_flags(m, c, s);
+      write_obs(m, c, s, cf);
+    }
+    WARP_FOR(i, od) a.obs[e * od + i] = s.obs[i];
+    IF_LANE0 { a.rew[e] = r.reward; a.term[e] = (uint8_t)r.terminated; a.trunc[e] = (uint8_t)r.truncated; }
+  } else if (a.op == OP_RESET) {
+    env_reset(m, c, s, a.opt, a.seed, a.env_base + (unsigned long long)e);
+    ContactFlags cf = contact_flags(m, c, s);
+    write_obs(m, c, s, cf);
+    if (a.obs) { WARP_FOR(i, od) a.obs[e * od + i] = s.obs[i]; }
+  } else if (a.op == OP_SET_STATE) {
+    WARP_FOR(i, m.nq) s.st.qpos[i] = a.qpos_in[e * m.nq + i];
+    WARP_FOR(i, m.nv) { s.st.qvel[i] = a.qvel_in[e * m.nv + i]; s.st.qacc_ws[i] = a.ws_in ? a.ws_in[e * m.nv + i] : Real(0); }
+    WARP_SYNC();
+    forward(m, s, a.opt, false);
+    update_cache(m, c, s);
+  } else {  // OP_DEBUG: full forward at the current state, dump internals of one environment
+    WARP_FOR(i, m.nu) s.ctrl[i] = 0;
+    WARP_SYNC();
+    forward(m, s, a.opt, true);
+    update_cache(m, c, s);
+    double* o = a.dbg;
+    const int nv = m.nv;
+    WARP_FOR(i, nv * nv) o[i] = (double)s.M[i / nv][i % nv];
+    o += MAXV * MAXV;
+    WARP_FOR(i, nv) { o[i] = (double)s.qfrc_bias[i]; o[MAXV + i] = (double)s.qacc[i]; o[2 * MAXV + i] = (double)s.qfrc_constraint[i]; }
+    o += 3 * MAXV;
+    IF_LANE0 { o[0] = s.ncon; o[1] = s.nefc; o[2] = s.solver_iter; o[3] = s.overflow; o[4] = s.ne; o[5] = s.nf; o[6] = s.nl; o[7] = 0; }
+    o += 8;
+    if constexpr (D::HAS_CONTACT) { WARP_FOR(i, s.ncon) { o[4 * i] = (double)s.con_dist[i]; for (int k = 0; k < 3; ++k) o[4 * i + 1 + k] = (double)s.con_pos[i][k]; } }
+    o += 4 * MAXCON;
+    WARP_FOR(i, CACHE_SIZE) o[i] = (double)s.st.cache[i];
+    return;  // debug does not modify the stored state
+  }
+  WARP_SYNC();
+  WARP_FOR(i, NW) gst[i] = sst[i];
+}
+
+template <typename Real, typename D>
+__global__ void state_io_kernel(EnvState<Real, D>* st, long long n, int nq, int nv, Real* qpos, Real* qvel, Real* ws) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long e = i / 64; int k = (int)(i % 64);
+  if (e >= n) return;
+  if (k < nq && qpos) qpos[e * nq + k] = st[e].qpos[k];
+  if (k < nv && qvel) qvel[e * nv + k] = st[e].qvel[k];
+  if (k < nv && ws) ws[e * nv + k] = st[e].qacc_ws[k];
+}
+
+template <typename Real, typename D>
+__global__ void stats_kernel(EnvState<Real, D>* st, long long n, double* out, int reset) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = 0; k < NSTAT; ++k) {
+    float v = e < n ? st[e].stat[k] : 0.f;
+    if (reset && e < n) st[e].stat[k] = 0.f;
+    double d = (double)v;
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    if ((threadIdx.x & 31) == 0 && d != 0.0) atomicAdd(out + k, d);
+  }
+}
+
+template <typename Real, typename D>
+struct Batch : BatchBase {
+  DevModel<Real>* d_model = nullptr;
+  EnvState<Real, D>* d_state = nullptr;
+  KArgs<Real, D> base;
+  HostModel hm;
+  int act_dim = 0, obs_dim = 0;
+  // staging for the host-buffer entry point
+  Real *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr; uint8_t *d_term = nullptr, *d_trunc = nullptr; double* d_dbg = nullptr;
+  cudaStream_t own_stream = nullptr;
+  uint64_t seed = 0;
+
+  ~Batch() override {
+    cudaSetDevice(device);
+    cudaFree(d_model); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+  int launch(KArgs<Real, D>& a, cudaStream_t s, long long envs) {
+    size_t smem = arena_stride<Real, D>() * WPB;
+    unsigned blocks = (unsigned)((envs + WPB - 1) / WPB);
+    env_kernel<Real, D><<<blocks, WPB * 32, smem, s>>>(a);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int init(const HostModel& h, const ur3e_env_config& cfg, long long n_envs, int dev) {
+    device = dev; n = n_envs; hm = h;
+    CUDA_OK(cudaSetDevice(dev));
+    DevModel<Real> m = compile_model<Real>(h);
+    CUDA_OK(cudaMalloc(&d_model, sizeof m)); CUDA_OK(cudaMemcpy(d_model, &m, sizeof m, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&d_state, sizeof(EnvState<Real, D>) * n_envs)); CUDA_OK(cudaMemset(d_state, 0, sizeof(EnvState<Real, D>) * n_envs));
+    std::memset(&base, 0, sizeof base);
+    EnvCfg<Real>& c = base.c;
+    c.ctrl_mode = cfg.ctrl_mode; c.obs_kind = cfg.obs_kind; c.reward_kind = cfg.reward_kind; c.term_kind = cfg.term_kind;
+    c.frame_skip = cfg.frame_skip; c.act_dim = cfg.act_dim; c.obs_dim = cfg.obs_dim; c.max_steps = cfg.max_steps;
+    c.reset_key = cfg.reset_key; c.reset_noise = cfg.reset_noise; c.auto_reset = cfg.auto_reset;
+    for (int k = 0; k < 24; ++k) c.gains[k] = (Real)cfg.gains[k];
+    for (int k = 0; k < 3; ++k) c.tool_rotvec[k] = (Real)cfg.tool_rotvec[k];
+    auto tracked = [&](const char* nm) { for (int k = 0; k < m.nsite; ++k) if (std::string(tracked_site_names()[k]) == nm) return k; return -1; };
+    c.site_tcp = tracked("tcp"); c.site_mug = tracked("handle_site"); c.site_pad = tracked("right_pad1_site");
+    c.body_mug = h.name2id(OBJ_BODY, "fish"); c.body_ghost = h.name2id(OBJ_BODY, "ghost");
+    c.body_lpad = h.name2id(OBJ_BODY, "left_pad"); c.body_rpad = h.name2id(OBJ_BODY, "right_pad"); c.body_table = h.name2id(OBJ_BODY, "table");
+    c.body_gripper_root = h.name2id(OBJ_BODY, "robotiq_base_mount"); c.body_gripper_last = -1;
+    if (c.body_gripper_root >= 0) {  // gym_utils.py:133-143: the subtree is a contiguous range in body order
+      const auto& par = h.I("body_parentid");
+      int last = c.body_gripper_root;
+      for (int b = c.body_gripper_root + 1; b < h.nbody; ++b) { int a = b; while (a > c.body_gripper_root) a = par[a]; if (a == c.body_gripper_root) last = b; else break; }
+      c.body_gripper_last = last;
+    }
+    c.finger_q = 6;  // utils/utils.py:319-326 reads d.qpos[6] / d.qvel[6]
+    c.topple_z = 0;
+    if (c.body_mug >= 0) {
+      for (int g = 0; g < h.ngeom; ++g) if (h.I("geom_bodyid")[g] == c.body_mug) {  // utils/utils.py:193-196 get_body_size = first geom
+        const double* sz = &h.D("geom_size")[3 * g];
+        for (int k = 0; k < 3; ++k) c.mug_size[k] = (Real)sz[k];
+        c.topple_z = (Real)(sz[0] > sz[1] ? sz[0] : sz[1]);
+        break;
+      }
+    }
+    bool needs_task = c.ctrl_mode == CTRL_PID_TASK || c.ctrl_mode == CTRL_PID_TASK_ENV;
+    if (needs_task && c.site_tcp < 0) return set_err("controller needs a 'tcp' site");
+    if (c.obs_kind != OBS_STATE && (c.site_tcp < 0 || c.site_mug < 0 || c.body_ghost < 0 || c.body_mug < 0)) return set_err("observation kind needs the tcp/handle_site sites and the fish/ghost bodies (main.xml)");
+    if (c.obs_kind == OBS_V0 && c.site_pad < 0) return set_err("OBS_V0 needs right_pad1_site");
+    int want_obs = c.obs_kind == OBS_STATE ? h.nq + h.nv : c.obs_kind == OBS_V2 ? 24 : 13;
+    if (c.obs_dim != want_obs || c.obs_dim > 32) return set_err("obs_dim does not match obs_kind (expected " + std::to_string(want_obs) + ")");
+    int want_act = c.ctrl_mode == CTRL_RAW ? h.nu : c.ctrl_mode == CTRL_PD_JOINT ? (h.nu > 6 ? 7 : 6) : c.ctrl_mode == CTRL_PID_TASK ? 7 : 4;
+    if (c.act_dim != want_act) return set_err("act_dim does not match ctrl_mode (expected " + std::to_string(want_act) + ")");
+    if (c.frame_skip < 1) return set_err("frame_skip must be >= 1");
+    if (c.reset_key >= h.nkey) return set_err("reset_key out of range");
+    const bool f64 = sizeof(Real) == 8;
+    base.opt.max_iter = cfg.solver_iterations > 0 ? cfg.solver_iterations : (f64 ? 50 : 8);
+    base.opt.tol = cfg.solver_tolerance > 0 ? (Real)cfg.solver_tolerance : (f64 ? Real(1e-15) : Real(1e-7));
+    base.opt.max_ls = f64 ? 50 : 12; base.opt.ls_tol = f64 ? Real(1e-14) : Real(1e-5);
+    base.m = d_model; base.st = d_state; base.n = n_envs; base.env_base = (unsigned long long)cfg.env_id_base;
+    act_dim = c.act_dim; obs_dim = c.obs_dim;
+    size_t smem = arena_stride<Real, D>() * WPB;
+    CUDA_OK(cudaFuncSetAttribute(env_kernel<Real, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa; CUDA_OK(cudaFuncGetAttributes(&fa, env_kernel<Real, D>));
+    regs = fa.numRegs; arena_bytes = (int)arena_stride<Real, D>();
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, env_kernel<Real, D>, WPB * 32, smem));
+    CUDA_OK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    return 0;
+  }
+  int reset(const uint8_t* mask, uint64_t sd, void* obs, cudaStream_t s) override {
+    CUDA_OK(cudaSetDevice(device));
+    seed = sd;
+    KArgs<Real, D> a = base; a.op = OP_RESET; a.mask = mask; a.seed = sd; a.obs = (Real*)obs;
+    return launch(a, s, n);
+  }
+  int step(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc, void* fobs, cudaStream_t s) override {
+    CUDA_OK(cudaSetDevice(device));
+    if (!act || !obs || !rew || !term || !trunc) return set_err("step: null buffer");
+    KArgs<Real, D> a = base; a.op = OP_STEP; a.seed = seed;
+    a.act = (const Real*)act; a.obs = (Real*)obs; a.rew = (Real*)rew; a.term = term; a.trunc = trunc; a.final_obs = (Real*)fobs;
+    return launch(a, s, n);
+  }
+  int ensure_staging() {
+    if (d_act) return 0;
+    CUDA_OK(cudaMalloc(&d_act, sizeof(Real) * n * act_dim)); CUDA_OK(cudaMalloc(&d_obs, sizeof(Real) * n * obs_dim));
+    CUDA_OK(cudaMalloc(&d_rew, sizeof(Real) * n)); CUDA_OK(cudaMalloc(&d_term, n)); CUDA_OK(cudaMalloc(&d_trunc, n));
+    return 0;
+  }
+  int step_host(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc) override {
+    CUDA_OK(cudaSetDevice(device));
+    if (int rc = ensure_staging()) return rc;
+    cudaStream_t s = own_stream;
+    CUDA_OK(cudaMemcpyAsync(d_act, act, sizeof(Real) * n * act_dim, cudaMemcpyHostToDevice, s));
+    if (int rc = step(d_act, d_obs, d_rew, d_term, d_trunc, nullptr, s)) return rc;
+    CUDA_OK(cudaMemcpyAsync(obs, d_obs, sizeof(Real) * n * obs_dim, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(rew, d_rew, sizeof(Real) * n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(term, d_term, n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaMemcpyAsync(trunc, d_trunc, n, cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+  }
+  int get_state(void* qpos, void* qvel, void* ws, cudaStream_t s) override {
+    CUDA_OK(cudaSetDevice(device));
+    long long tot = n * 64;
+    state_io_kernel<Real, D><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_state, n, hm.nq, hm.nv, (Real*)qpos, (Real*)qvel, (Real*)ws);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int set_state(const void* qpos, const void* qvel, const void* ws, cudaStream_t s) override {
+    CUDA_OK(cudaSetDevice(device));
+    if (!qpos || !qvel) return set_err("set_state: null buffer");
+    KArgs<Real, D> a = base; a.op = OP_SET_STATE; a.qpos_in = (const Real*)qpos; a.qvel_in = (const Real*)qvel; a.ws_in = (const Real*)ws;
+    return launch(a, s, n);
+  }
+  int stats(double* out, int rst, cudaStream_t s) override {
+    CUDA_OK(cudaSetDevice(device));
+    CUDA_OK(cudaMemsetAsync(out, 0, 16 * sizeof(double), s));
+    stats_kernel<Real, D><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_state, n, out, rst);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  int debug(long long env, double* M, double* bias, double* qacc, double* fc, int32_t* info, double* con, double* cache) override {
+    CUDA_OK(cudaSetDevice(device));
+    if (env < 0 || env >= n) return set_err("debug: env out of range");
+    if (!d_dbg) CUDA_OK(cudaMalloc(&d_dbg, sizeof(double) * DBG_DOUBLES));
+    CUDA_OK(cudaMemset(d_dbg, 0, sizeof(double) * DBG_DOUBLES));
+    KArgs<Real, D> a = base; a.op = OP_DEBUG; a.dbg_env = env; a.dbg = d_dbg;
+    if (int rc = launch(a, 0, 1)) return rc;
+    std::vector<double> hbuf(DBG_DOUBLES);
+    CUDA_OK(cudaMemcpy(hbuf.data(), d_dbg, sizeof(double) * DBG_DOUBLES, cudaMemcpyDeviceToHost));
+    const int nv = hm.nv; const double* o = hbuf.data();
+    if (M) std::memcpy(M, o, sizeof(double) * nv * nv);
+    o += MAXV * MAXV;
+    if (bias) std::memcpy(bias, o, sizeof(double) * nv);
+    if (qacc) std::memcpy(qacc, o + MAXV, sizeof(double) * nv);
+    if (fc) std::memcpy(fc, o + 2 * MAXV, sizeof(double) * nv);
+    o += 3 * MAXV;
+    if (info) for (int k = 0; k < 8; ++k) info[k] = (int32_t)o[k];
+    o += 8;
+    if (con) std::memcpy(con, o, sizeof(double) * 4 * MAXCON);
+    o += 4 * MAXCON;
+    if (cache) std::memcpy(cache, o, sizeof(double) * CACHE_SIZE);
+    return 0;
+  }
+};
+
+
+template <typename Real, typename D>
+std::unique_ptr<BatchBase> make_batch(const HostModel& h, const ur3e_env_config& cfg, long long n, int device) {
+  auto p = std::make_unique<Batch<Real, D>>();
+  if (p->init(h, cfg, n, device)) return nullptr;
+  return p;
+}
+
+}  // namespace ur3e

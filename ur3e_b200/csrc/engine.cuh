@@ -26,9 +26,24 @@ constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 
 enum RowType { ROW_EQ = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_CON_N = 3, ROW_CON_T1 = 4, ROW_CON_T2 = 5 };
 
+// Persistent per-environment record (lives in HBM between launches, one contiguous 16-byte aligned block per
+// environment so that a warp loads/stores it with coalesced 128-bit accesses).
+constexpr int NSTAT = 14;
+enum StatSlot { ST_EPISODES = 0, ST_RETURN, ST_LENGTH, ST_SUCCESS, ST_TERM_REACH, ST_TERM_TOPPLE, ST_TERM_COLLISION, ST_TRUNC, ST_UNSTABLE,
+                ST_NEFC, ST_NCON, ST_ITER, ST_SUBSTEPS, ST_OVERFLOW };
+template <typename Real, typename D>
+struct alignas(16) EnvState {
+  Real qpos[D::NQ], qvel[D::NV], qacc_ws[D::NV];
+  Real cache[CACHE_SIZE];   // stale-kinematics cache read by the next step's controller
+  Real ep_return;
+  float stat[NSTAT];        // counters since the last ur3e_batch_stats(reset)
+  int t, episode;
+};
+
 template <typename Real, typename D>
 struct Arena {
-  Real qpos[D::NQ], qvel[D::NV], qacc[D::NV], qacc_ws[D::NV], ctrl[D::NU], act_force[D::NU];
+  EnvState<Real, D> st;
+  Real qacc[D::NV], ctrl[D::NU], act_force[D::NU], obs[32];
   Real xpos[D::NB][3], xquat[D::NB][4], xmat[D::NB][9], xipos[D::NB][3];
   Real cdof[D::NV][6];
   Real M[D::NV][D::NV];
@@ -47,7 +62,6 @@ struct Arena {
     Real stage[D::NPAIR][STAGE_PTS][7];  // pos 3, normal 3, dist
     Real efc_J[D::MAXEFC][D::NV];
   } u;
-  Real cache[CACHE_SIZE];
 };
 
 // ---------------------------------------------------------------- scalar math
@@ -133,8 +147,8 @@ UR3E_HD void fk_body(const DevModel<Real>& m, Arena<Real, D>& s, int b) {
   Real pos[3], quat[4];
   if (jk == JK_FREE) {
     int qa = m.body_qadr[b], da = m.body_dadr[b];
-    for (int k = 0; k < 3; ++k) pos[k] = s.qpos[qa + k];
-    for (int k = 0; k < 4; ++k) quat[k] = s.qpos[qa + 3 + k];
+    for (int k = 0; k < 3; ++k) pos[k] = s.st.qpos[qa + k];
+    for (int k = 0; k < 4; ++k) quat[k] = s.st.qpos[qa + 3 + k];
     quat_normalize(quat);
     Real R[9]; quat2mat(R, quat);
     for (int i = 0; i < 3; ++i) {
@@ -154,7 +168,7 @@ UR3E_HD void fk_body(const DevModel<Real>& m, Arena<Real, D>& s, int b) {
       mat_vec3(vec, R0, m.jnt_pos[b]);
       for (int k = 0; k < 3; ++k) anchor[k] = pos[k] + vec[k];
       mat_vec3(axis, R0, m.jnt_axis[b]);
-      Real ang = s.qpos[m.body_qadr[b]] - m.jnt_q0[b], sn = Num<Real>::sin(ang * Real(0.5)), cs = Num<Real>::cos(ang * Real(0.5));
+      Real ang = s.st.qpos[m.body_qadr[b]] - m.jnt_q0[b], sn = Num<Real>::sin(ang * Real(0.5)), cs = Num<Real>::cos(ang * Real(0.5));
       Real ql[4] = {cs, m.jnt_axis[b][0] * sn, m.jnt_axis[b][1] * sn, m.jnt_axis[b][2] * sn};
       quat_mul(quat, quat, ql);
       quat_normalize(quat);
@@ -231,7 +245,7 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
       ci[3] = t01 - mass * dif[0] * dif[1]; ci[4] = t02 - mass * dif[0] * dif[2]; ci[5] = t12 - mass * dif[1] * dif[2];
       ci[6] = mass * dif[0]; ci[7] = mass * dif[1]; ci[8] = mass * dif[2]; ci[9] = mass;
       Real cv[6] = {0, 0, 0, 0, 0, 0};
-      for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { Real qd = s.qvel[d]; for (int k = 0; k < 6; ++k) cv[k] += s.cdof[d][k] * qd; }
+      for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { Real qd = s.st.qvel[d]; for (int k = 0; k < 6; ++k) cv[k] += s.cdof[d][k] * qd; }
       for (int k = 0; k < 6; ++k) y.cvel[b][k] = cv[k];
     }
   }
@@ -250,7 +264,7 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
     else {
       Real vel[6];
       for (int k = 0; k < 6; ++k) vel[k] = y.cvel[m.body_parent[b]][k];
-      if (fk >= 3) { int da = m.body_dadr[b]; for (int i = 0; i < 3; ++i) for (int k = 0; k < 6; ++k) vel[k] += s.cdof[da + i][k] * s.qvel[da + i]; }
+      if (fk >= 3) { int da = m.body_dadr[b]; for (int i = 0; i < 3; ++i) for (int k = 0; k < 6; ++k) vel[k] += s.cdof[da + i][k] * s.st.qvel[da + i]; }
       cross_motion(cd, vel, s.cdof[d]);
     }
   }
@@ -263,7 +277,7 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
     if (b == 0 || m.body_lastdof[b] < 0) { for (int k = 0; k < 6; ++k) f[k] = 0; }
     else {
       Real a[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
-      for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { Real qd = s.qvel[d]; for (int k = 0; k < 6; ++k) a[k] += y.cdof_dot[d][k] * qd; }
+      for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { Real qd = s.st.qvel[d]; for (int k = 0; k < 6; ++k) a[k] += y.cdof_dot[d][k] * qd; }
       Real t1[6], t2[6];
       mul_inert(f, y.cinert[b], a);
       mul_inert(t1, y.cinert[b], y.cvel[b]); cross_force(t2, y.cvel[b], t1);
@@ -295,7 +309,7 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
     Real c = s.ctrl[a];
     if (m.act_ctrllimited[a]) c = rmin(rmax(c, m.act_ctrlrange[a][0]), m.act_ctrlrange[a][1]);
     Real len = 0, vel = 0;
-    for (int k = 0; k < 2; ++k) { int d = m.act_dof[a][k]; if (d >= 0) { len += m.act_coef[a][k] * s.qpos[m.dof_qadr[d]]; vel += m.act_coef[a][k] * s.qvel[d]; } }
+    for (int k = 0; k < 2; ++k) { int d = m.act_dof[a][k]; if (d >= 0) { len += m.act_coef[a][k] * s.st.qpos[m.dof_qadr[d]]; vel += m.act_coef[a][k] * s.st.qvel[d]; } }
     Real f = m.act_gain[a] * c + m.act_bias[a][0] + m.act_bias[a][1] * len + m.act_bias[a][2] * vel;
     if (m.act_forcelimited[a]) f = rmin(rmax(f, m.act_forcerange[a][0]), m.act_forcerange[a][1]);
     s.act_force[a] = f;
@@ -304,8 +318,8 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
   WARP_FOR(d, nv) {
     Real bias = 0; for (int k = 0; k < 6; ++k) bias += s.cdof[d][k] * y.cfrc[m.dof_body[d]][k];
     s.qfrc_bias[d] = bias;
-    Real f = -m.dof_damping[d] * s.qvel[d];
-    if (m.dof_free_k[d] < 0) f -= m.dof_stiffness[d] * (s.qpos[m.dof_qadr[d]] - m.dof_springref[d]);
+    Real f = -m.dof_damping[d] * s.st.qvel[d];
+    if (m.dof_free_k[d] < 0) f -= m.dof_stiffness[d] * (s.st.qpos[m.dof_qadr[d]] - m.dof_springref[d]);
     for (int a = 0; a < m.nu; ++a) for (int k = 0; k < 2; ++k) if (m.act_dof[a][k] == d) f += m.act_coef[a][k] * s.act_force[a];
     s.qfrc_smooth[d] = f - bias;
   }
@@ -521,7 +535,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   int mlo = 0, mhi = 0;   // bit d: lower / upper limit of dof d is active (dist < margin)
   WARP_FOR(d, nv) {
     if (m.dof_limited[d]) {
-      Real q = s.qpos[m.dof_qadr[d]];
+      Real q = s.st.qpos[m.dof_qadr[d]];
       if ((q - m.dof_range[d][0]) < m.dof_margin[d]) mlo |= 1 << d;
       if ((m.dof_range[d][1] - q) < m.dof_margin[d]) mhi |= 1 << d;
     }
@@ -554,9 +568,9 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
         IF_LANE0 {
           int d1 = m.eq_o1[e], d2 = m.eq_o2[e];
           const Real* c = m.eq_data[e];
-          Real p1 = s.qpos[m.dof_qadr[d1]] - m.qpos0[m.dof_qadr[d1]], pos, deriv = 0;
+          Real p1 = s.st.qpos[m.dof_qadr[d1]] - m.qpos0[m.dof_qadr[d1]], pos, deriv = 0;
           if (d2 >= 0) {
-            Real p2 = s.qpos[m.dof_qadr[d2]] - m.qpos0[m.dof_qadr[d2]];
+            Real p2 = s.st.qpos[m.dof_qadr[d2]] - m.qpos0[m.dof_qadr[d2]];
             pos = p1 - (c[0] + p2 * (c[1] + p2 * (c[2] + p2 * (c[3] + p2 * c[4]))));
             deriv = c[1] + p2 * (2 * c[2] + p2 * (3 * c[3] + p2 * 4 * c[4]));
             s.u.efc_J[row][d2] = -deriv;
@@ -579,7 +593,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
       int below = (1 << d) - 1;
       int r = ne + nf + popcount32(mlo & below) + popcount32(mhi & below) + (k == 1 ? ((mlo >> d) & 1) : 0);
       if (r < D::MAXEFC) {
-        Real q = s.qpos[m.dof_qadr[d]];
+        Real q = s.st.qpos[m.dof_qadr[d]];
         s.u.efc_J[r][d] = k == 0 ? Real(1) : Real(-1);
         s.efc_aref[r] = k == 0 ? q - m.dof_range[d][0] : m.dof_range[d][1] - q;
         s.efc_R[r] = m.dof_margin[d]; s.efc_type[r] = ROW_LIMIT; s.efc_id[r] = d; s.efc_fl[r] = 0;
@@ -629,7 +643,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
       else R = R1 * m.pair_friction[p][0] * m.pair_friction[p][0] / (m.pair_friction[p][1] * m.pair_friction[p][1]);
     }
     if (fric) K = 0;
-    Real vel = 0; for (int k = 0; k < nv; ++k) vel += s.u.efc_J[r][k] * s.qvel[k];
+    Real vel = 0; for (int k = 0; k < nv; ++k) vel += s.u.efc_J[r][k] * s.st.qvel[k];
     s.efc_R[r] = R; s.efc_D[r] = 1 / R;
     s.efc_aref[r] = -B * vel - K * imp * (pos - margin);
   }
@@ -760,7 +774,7 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
     return;
   }
   const Real scale = Real(1) / (m.meaninertia * Real(nv > 1 ? nv : 1));
-  WARP_FOR(d, nv) s.qacc[d] = s.qacc_ws[d];
+  WARP_FOR(d, nv) s.qacc[d] = s.st.qacc_ws[d];
   WARP_SYNC();
   WARP_FOR(i, nv + nefc) {
     if (i < nv) { Real v = 0; for (int k = 0; k < nv; ++k) v += s.M[i][k] * s.qacc[k]; s.Ma[i] = v; }
@@ -850,8 +864,8 @@ UR3E_HD void forward(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpt
 
 template <typename Real, typename D>
 UR3E_HD void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
-  WARP_FOR(i, m.nq) s.qpos[i] = m.qpos0[i];
-  WARP_FOR(i, m.nv) { s.qvel[i] = 0; s.qacc_ws[i] = 0; s.qacc[i] = 0; }
+  WARP_FOR(i, m.nq) s.st.qpos[i] = m.qpos0[i];
+  WARP_FOR(i, m.nv) { s.st.qvel[i] = 0; s.st.qacc_ws[i] = 0; s.qacc[i] = 0; }
   WARP_FOR(i, m.nu) s.ctrl[i] = 0;
   WARP_SYNC();
 }
@@ -872,19 +886,19 @@ UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
     chol_solve_aug(s, nv, s.search);
     qa = s.search;
   }
-  WARP_FOR(d, nv) s.qvel[d] += h * qa[d];
+  WARP_FOR(d, nv) s.st.qvel[d] += h * qa[d];
   WARP_SYNC();
   WARP_FOR(d, nv) {
     int fk = m.dof_free_k[d], q = m.dof_qadr[d];
-    if (fk < 0 || fk < 3) s.qpos[q] += h * s.qvel[d];
+    if (fk < 0 || fk < 3) s.st.qpos[q] += h * s.st.qvel[d];
     else if (fk == 3) {
-      Real w[3] = {s.qvel[d], s.qvel[d + 1], s.qvel[d + 2]};
+      Real w[3] = {s.st.qvel[d], s.st.qvel[d + 1], s.st.qvel[d + 2]};
       Real n = Num<Real>::sqrt(dot3(w, w)), ang = h * n;
       Real qr[4] = {1, 0, 0, 0};
       if (n >= Num<Real>::minval && ang != 0) { Real sn = Num<Real>::sin(ang * Real(0.5)) / n; qr[0] = Num<Real>::cos(ang * Real(0.5)); qr[1] = w[0] * sn; qr[2] = w[1] * sn; qr[3] = w[2] * sn; }
-      Real qq[4] = {s.qpos[q], s.qpos[q + 1], s.qpos[q + 2], s.qpos[q + 3]}, out[4];
+      Real qq[4] = {s.st.qpos[q], s.st.qpos[q + 1], s.st.qpos[q + 2], s.st.qpos[q + 3]}, out[4];
       quat_normalize(qq); quat_mul(out, qq, qr);
-      for (int k = 0; k < 4; ++k) s.qpos[q + k] = out[k];
+      for (int k = 0; k < 4; ++k) s.st.qpos[q + k] = out[k];
     }
   }
   WARP_SYNC();
@@ -894,7 +908,7 @@ UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
 template <typename Real, typename D>
 UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
   int w = 0;
-  WARP_FOR(i, m.nq + m.nv) w |= i < m.nq ? is_bad(s.qpos[i]) : 2 * is_bad(s.qvel[i - m.nq]);
+  WARP_FOR(i, m.nq + m.nv) w |= i < m.nq ? is_bad(s.st.qpos[i]) : 2 * is_bad(s.st.qvel[i - m.nq]);
   w = warp_or(w);
   if (w) reset_data(m, s);
   forward(m, s, opt, true);
@@ -902,7 +916,7 @@ UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts
   WARP_FOR(i, m.nv) wa |= 4 * is_bad(s.qacc[i]);
   wa = warp_or(wa);
   if (wa) { reset_data(m, s); forward(m, s, opt, true); w |= wa; }
-  WARP_FOR(d, m.nv) s.qacc_ws[d] = s.qacc[d];
+  WARP_FOR(d, m.nv) s.st.qacc_ws[d] = s.qacc[d];
   WARP_SYNC();
   euler(m, s);
   return w;
