@@ -82,7 +82,6 @@ def test_main_forward_internals_f64(assets):
     rng = np.random.default_rng(3)
     n = 8
     qp, qv = _random_states(m, rng, n)
-    b = make(assets, "main.xml", n, torch.float64, ctrl_mode=lib.CTRL_RAW, obs_kind=lib.OBS_STATE, obs_dim=32 if False else 41 - 9, act_dim=7) if False else None
     b = make(assets, "main.xml", n, torch.float64, ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2, reset_key=1, term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500)
     b.reset()
     b.set_state(torch.tensor(qp, device="cuda"), torch.tensor(qv, device="cuda"))
@@ -156,15 +155,20 @@ def test_auto_reset_and_stats(assets):
     assert o0[:, 3].std() > 0 and o0[:, 4].std() > 0            # mug x,y noise differs per env
     assert (o0[:, 3] >= 0.29799994 - 1e-6).all() and (o0[:, 3] <= 0.31799994 + 1e-6).all()
     a = torch.cat([o0[:, 0:3], torch.zeros(n, 1, device="cuda")], 1).contiguous()
-    ndone = 0
+    ndone, lens, tlen = 0, torch.zeros(n, device="cuda"), 0.0
     for k in range(10):
         obs, rew, term, trunc = b.step(a)
-        ndone += int((term | trunc).sum().item())
-        if k == 4:
-            assert trunc.all()
+        done = (term | trunc).bool()
+        lens += 1
+        ndone += int(done.sum().item()); tlen += float(lens[done].sum().item()); lens[done] = 0
+        assert (lens <= 5).all()                                 # nobody outlives max_steps
+        # a finished env returns its reset observation (tcp back at the keyframe) and keeps the terminal one in final_obs
+        if done.any():
+            assert (obs[done][:, 0:3] - o0[done][:, 0:3]).abs().max() < 1e-5
+    assert ndone >= n                                            # every env was truncated at least once in 10 steps
     st = b.stats_dict()
     assert st["episodes"] == ndone and st["substeps"] == n * 10 * 2
-    assert st["length_sum"] == 5 * ndone
+    assert st["length_sum"] == tlen
 
 
 def test_host_entry_point(assets):
