@@ -125,7 +125,8 @@ class SimBatch:
     def kernel_info(self):
         v = [C.c_int32() for _ in range(4)]
         _lib.check(self._L.ur3e_batch_kernel_info(self.ptr, *[C.byref(x) for x in v]), "ur3e_batch_kernel_info")
-        return dict(arena_bytes=v[0].value, warps_per_block=v[1].value, blocks_per_sm=v[2].value, regs_per_thread=v[3].value)
+        return dict(arena_bytes=v[0].value, warps_per_block=v[1].value, blocks_per_sm=v[2].value, regs_per_thread=v[3].value,
+                    state_bytes=int(self._L.ur3e_batch_state_bytes(self.ptr)))
 
     def close(self):
         if getattr(self, "ptr", None):

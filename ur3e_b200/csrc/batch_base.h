@@ -29,7 +29,7 @@ struct BatchBase {
   virtual int stats(double* out, int reset, cudaStream_t s) = 0;
   virtual int debug(long long env, double* M, double* bias, double* qacc, double* fc, int32_t* info, double* con, double* cache) = 0;
   int64_t launches = 0;
-  int arena_bytes = 0, blocks_per_sm = 0, regs = 0, device = 0;
+  int arena_bytes = 0, blocks_per_sm = 0, regs = 0, device = 0, state_bytes = 0;
   long long n = 0;
 };
 

@@ -192,7 +192,7 @@ struct Batch : BatchBase {
     size_t smem = arena_stride<Real, D>() * WPB;
     CUDA_OK(cudaFuncSetAttribute(env_kernel<Real, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa; CUDA_OK(cudaFuncGetAttributes(&fa, env_kernel<Real, D>));
-    regs = fa.numRegs; arena_bytes = (int)arena_stride<Real, D>();
+    regs = fa.numRegs; arena_bytes = (int)arena_stride<Real, D>(); state_bytes = (int)sizeof(EnvState<Real, D>);
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, env_kernel<Real, D>, WPB * 32, smem));
     CUDA_OK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     return 0;

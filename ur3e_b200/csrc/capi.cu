@@ -93,5 +93,6 @@ int ur3e_batch_kernel_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t* w
   if (arena_bytes) *arena_bytes = b->impl->arena_bytes; if (wpb) *wpb = WPB; if (blocks_per_sm) *blocks_per_sm = b->impl->blocks_per_sm; if (regs) *regs = b->impl->regs;
   return 0;
 }
+int ur3e_batch_state_bytes(const ur3e_batch* b) { return (b && b->impl) ? b->impl->state_bytes : -1; }
 
 }  // extern "C"
