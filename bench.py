@@ -99,7 +99,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per = args.cpu_steps or 1500
+    per = args.cpu_steps or 8000
     t_all = []
     total_steps = 0
     for _ in range(max(1, min(args.steps, 3))):    # bounded: a few samples, each ~ per x cores env-steps
@@ -276,7 +276,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        per = args.cpu_steps or 2500
+        per = args.cpu_steps or 80000
         rate, procs, total, wall = cpu_leg(args.workload, per, cores)
         cpu = {"value": rate, "unit": UNIT, "cores": procs, "kind": "port",
                "sample": "%d processes x %d ur3e-v2 env-steps of the float64 oracle restatement (%.1f s wall); MuJoCo 3.3.3 is not installable here" % (procs, per, wall)}

@@ -16,13 +16,15 @@ LIB = os.path.join(HERE, "libur3e_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH
+# float32 production units: approximate division / sqrt (2 ulp) and flush-to-zero; sin/cos stay exact. float64 validation units keep IEEE.
+F32_FLAGS = ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]
 UNITS = ["capi.cu", "mjcf.cpp"] + ["inst_%s_%s.cu" % (r, d) for r in ("f32", "f64") for d in ("raw", "grip", "main")]
 HEADERS = ["batch_base.h", "batch_impl.cuh", "compile_model.h", "dev_model.h", "engine.cuh", "env.cuh", "host_model.h",
            "warp_model.cuh", "xml_mini.h", os.path.join("..", "..", "include", "ur3e_b200.h")]
 
 
 def _digest(unit):
-    h = hashlib.sha256(" ".join(FLAGS).encode())
+    h = hashlib.sha256(" ".join(FLAGS + F32_FLAGS).encode())
     deps = [unit] + (HEADERS if unit != "mjcf.cpp" else ["host_model.h", "xml_mini.h"])
     for f in deps:
         with open(os.path.join(CSRC, f), "rb") as fh:
@@ -36,7 +38,8 @@ def _compile(unit, verbose):
     dig = _digest(unit)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, False, ""
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, unit), "-o", obj]
+    extra = F32_FLAGS if unit.startswith("inst_f32") else []
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, unit), "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s" % (unit, p.stderr[-4000:]))

@@ -17,7 +17,6 @@ inline int set_err(const std::string& e, int code = -1) { g_err = e; return code
 #define CUDA_OK(expr)                                                                                       \
   do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return ::ur3e::set_err(std::string(#expr) + ": " + cudaGetErrorString(e_), -2); } while (0)
 
-constexpr int WPB = 4;  // warps (environments) per block
 
 struct BatchBase {
   virtual ~BatchBase() {}
@@ -29,7 +28,7 @@ struct BatchBase {
   virtual int stats(double* out, int reset, cudaStream_t s) = 0;
   virtual int debug(long long env, double* M, double* bias, double* qacc, double* fc, int32_t* info, double* con, double* cache) = 0;
   int64_t launches = 0;
-  int arena_bytes = 0, blocks_per_sm = 0, regs = 0, device = 0, state_bytes = 0;
+  int arena_bytes = 0, blocks_per_sm = 0, regs = 0, device = 0, state_bytes = 0, wpb = 0;
   long long n = 0;
 };
 

@@ -28,10 +28,23 @@ struct KArgs {
 };
 
 template <typename Real, typename D> __host__ __device__ constexpr size_t arena_stride() { return (sizeof(Arena<Real, D>) + 15) / 16 * 16; }
+// warps (environments) per block: the value in {1,2,4} that fits most warps into the 228 KB of an SM (1 KB is reserved per block)
+template <typename Real, typename D> __host__ __device__ constexpr int warps_per_block() {
+  int best = 1, best_w = 0;
+  for (int w = 4; w >= 1; w >>= 1) {
+    size_t per_block = arena_stride<Real, D>() * w + 1024;
+    if (arena_stride<Real, D>() * w > 232448) continue;
+    int warps = (int)(233472 / per_block) * w;
+    if (warps > 64) warps = 64;
+    if (warps > best_w) { best_w = warps; best = w; }
+  }
+  return best;
+}
 constexpr int DBG_DOUBLES = MAXV * MAXV + 3 * MAXV + 8 + 4 * MAXCON + CACHE_SIZE;
 
 template <typename Real, typename D>
-__global__ void __launch_bounds__(WPB * 32) env_kernel(const KArgs<Real, D> a) {
+__global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(const KArgs<Real, D> a) {
+  constexpr int WPB = warps_per_block<Real, D>();
   extern __shared__ int4 smem_raw[];
   const int warp = threadIdx.x >> 5;
   long long e = (long long)blockIdx.x * WPB + warp;
@@ -131,6 +144,7 @@ struct Batch : BatchBase {
     cudaFree(d_model); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
+  static constexpr int WPB = warps_per_block<Real, D>();
   int launch(KArgs<Real, D>& a, cudaStream_t s, long long envs) {
     size_t smem = arena_stride<Real, D>() * WPB;
     unsigned blocks = (unsigned)((envs + WPB - 1) / WPB);
@@ -187,12 +201,13 @@ struct Batch : BatchBase {
     base.opt.max_iter = cfg.solver_iterations > 0 ? cfg.solver_iterations : (f64 ? 50 : 8);
     base.opt.tol = cfg.solver_tolerance > 0 ? (Real)cfg.solver_tolerance : (f64 ? Real(1e-15) : Real(1e-7));
     base.opt.max_ls = f64 ? 50 : 12; base.opt.ls_tol = f64 ? Real(1e-14) : Real(1e-5);
+    base.opt.rtol = f64 ? Real(1e-15) : Real(2e-6);
     base.m = d_model; base.st = d_state; base.n = n_envs; base.env_base = (unsigned long long)cfg.env_id_base;
     act_dim = c.act_dim; obs_dim = c.obs_dim;
     size_t smem = arena_stride<Real, D>() * WPB;
     CUDA_OK(cudaFuncSetAttribute(env_kernel<Real, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa; CUDA_OK(cudaFuncGetAttributes(&fa, env_kernel<Real, D>));
-    regs = fa.numRegs; arena_bytes = (int)arena_stride<Real, D>(); state_bytes = (int)sizeof(EnvState<Real, D>);
+    wpb = WPB; regs = fa.numRegs; arena_bytes = (int)arena_stride<Real, D>(); state_bytes = (int)sizeof(EnvState<Real, D>);
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, env_kernel<Real, D>, WPB * 32, smem));
     CUDA_OK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     return 0;

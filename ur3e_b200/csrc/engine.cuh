@@ -759,7 +759,7 @@ UR3E_HD void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real al
   *ddphi = g2 + warp_sum(p2);
 }
 
-template <typename Real> struct SolverOpts { int max_iter; int max_ls; Real tol; Real ls_tol; };
+template <typename Real> struct SolverOpts { int max_iter; int max_ls; Real tol; Real ls_tol; Real rtol; };
 
 template <typename Real, typename D>
 UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
@@ -784,14 +784,16 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
   int iter = 0;
   for (; iter < opt.max_iter; ++iter) {
     constraint_update(m, s, true);
-    Real gg = 0;
+    Real gg = 0, gref = 0;
     WARP_FOR(d, nv) {
-      Real g = s.Ma[d] - s.qfrc_smooth[d];
-      for (int r = 0; r < nefc; ++r) g -= s.u.efc_J[r][d] * s.efc_force[r];
-      s.grad[d] = g; gg += g * g;
+      Real g = s.Ma[d] - s.qfrc_smooth[d], fc = 0;
+      for (int r = 0; r < nefc; ++r) fc += s.u.efc_J[r][d] * s.efc_force[r];
+      g -= fc;
+      s.grad[d] = g; gg += g * g; gref += s.Ma[d] * s.Ma[d] + s.qfrc_smooth[d] * s.qfrc_smooth[d] + fc * fc;
     }
-    gg = warp_sum(gg);
-    if (scale * Num<Real>::sqrt(gg) < opt.tol) break;
+    gg = warp_sum(gg); gref = warp_sum(gref);
+    // converged: MuJoCo's scaled-gradient test, or the gradient is at the rounding floor of its own terms
+    if (scale * Num<Real>::sqrt(gg) < opt.tol || gg < opt.rtol * opt.rtol * gref) break;
     // H = M + J^T diag(Dact) J + cone blocks ; augmented row = -grad
     WARP_FOR(e, (nv + 1) * (nv + 2) / 2) {
       int ab = m.tri_ab[e], a = ab >> 8, b = ab & 255;   // (a, b), b <= a, over the (nv+1) x (nv+1) lower triangle
