@@ -1,0 +1,109 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by running the REFERENCE's own Python verbatim (from /root/reference) on
+top of the oracle through oracle/refshim.py.  Run in the build container only:
+
+    python tools/make_golden.py
+
+What the fixtures pin: the reference's controller / observation / reward / termination / truncation code
+(controller_func.py, gym_utils.py, ur3e_env2.py, ur3e_env.py, imitation_env_*.py) executed as written,
+including scipy's Rotation conventions and the stale-kinematics order of reads.  What they do NOT pin: the
+physics, which is the oracle's restatement of mj_step (MuJoCo is not installable here).
+"""
+import io
+import os
+import sys
+import contextlib
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+from oracle import refshim  # noqa: E402
+
+uu, cf, gu = refshim.import_reference()
+import yaml  # noqa: E402
+
+
+def env_episode(cls_name, module, steps, seed, direct=False):
+    mod = __import__(module, fromlist=[cls_name])
+    np.random.seed(seed)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        env = getattr(mod, cls_name)()
+        obs0, _ = env.reset()
+    qpos0, qvel0 = env.data.qpos.copy(), env.data.qvel.copy()
+    rng = np.random.default_rng(seed)
+    rec = dict(qpos0=qpos0, qvel0=qvel0, obs0=np.asarray(obs0, dtype=np.float64), actions=[], obs=[], reward=[], terminated=[], truncated=[], qpos=[], qvel=[],
+               action_low=np.asarray(env.action_space.low, dtype=np.float64), action_high=np.asarray(env.action_space.high, dtype=np.float64),
+               frame_skip=np.int64(env.frame_skip))
+    mug = obs0[3:6].copy()
+    for k in range(steps):
+        if direct:
+            a = np.zeros(7); a[:6] = rng.uniform(-2, 2, 6); a[6] = 255.0 if k > steps // 2 else 0.0
+        else:
+            # scripted approach, close, lift: exercises pad-mug contacts, grasp flags and the reward branches
+            z = mug[2] + 0.02 + max(0.0, 0.1 - 0.002 * k) + (0.0 if k < 170 else 0.0005 * (k - 170))
+            a = np.hstack([mug[:2] + rng.normal(0, 0.001, 2), z, 1.0 if k > 90 else 0.0])
+        with contextlib.redirect_stdout(sink):
+            o, r, te, tr, _ = env.step(a)
+        rec["actions"].append(a); rec["obs"].append(np.asarray(o, dtype=np.float64)); rec["reward"].append(float(r))
+        rec["terminated"].append(bool(te)); rec["truncated"].append(bool(tr)); rec["qpos"].append(env.data.qpos.copy()); rec["qvel"].append(env.data.qvel.copy())
+        if te or tr:
+            break
+    return {k: np.asarray(v) for k, v in rec.items()}
+
+
+def controller_vectors(seed):
+    """pid_task_ctrl / pd_joint_ctrl / get_rot_err of the reference on random ur3e_2f85.xml states."""
+    import mujoco
+    m, d = uu.load_model("assets/ur3e_2f85.xml")
+    rng = np.random.default_rng(seed)
+    with open("controller/config/config_l_task.yml") as f:
+        yml = yaml.safe_load(f)
+    pos_g = {k: np.diag(v) for k, v in yml["pos"].items()}; rot_g = {k: np.diag(v) for k, v in yml["rot"].items()}
+    with open("controller/config/config_j.yml") as f:
+        yj = yaml.safe_load(f)
+    jg = {k: np.diag(v) for k, v in yj["qpos"].items()}     # move_j.py:50
+    from controller.move_j import ctrl as move_j_ctrl      # move_j.py:14-27 (pd_joint_ctrl + grip_ctrl)
+    out = dict(qpos=[], qvel=[], traj=[], u_task=[], rot_err=[], target_j=[], u_joint=[])
+    for _ in range(24):
+        uu.reset(m, d, "down")
+        d.qpos[:6] += rng.uniform(-0.5, 0.5, 6); d.qvel[:] = rng.uniform(-1, 1, m.nv)
+        mujoco.mj_forward(m, d)
+        tcp = uu.get_site_xpos(m, d, "tcp")
+        traj = np.hstack([tcp + rng.uniform(-0.1, 0.1, 3), rng.uniform(-2.5, 2.5, 3), rng.uniform(0, 1)])
+        u = cf.pid_task_ctrl(0, m, d, traj, pos_g, rot_g, np.zeros((1, 3)), np.zeros((1, 3)), np.zeros(3), np.zeros(3))
+        e = cf.get_rot_err(0, m, d, traj[3:6], np.zeros((1, 3)))
+        tj = np.hstack([d.qpos[:6] + rng.uniform(-0.2, 0.2, 6), 0.3])
+        uj = move_j_ctrl(0, m, d, tj, jg, np.zeros((1, 6)))
+        out["qpos"].append(d.qpos.copy()); out["qvel"].append(d.qvel.copy()); out["traj"].append(traj); out["u_task"].append(u)
+        out["rot_err"].append(e); out["target_j"].append(tj); out["u_joint"].append(uj)
+    g = dict(gains_task=np.hstack([np.diag(pos_g["kp"]), np.diag(pos_g["kd"]), np.diag(rot_g["kp"]), np.diag(rot_g["kd"])]))
+    if jg:
+        g["gains_j"] = np.hstack([np.diag(jg["kp"]), np.diag(jg["kd"])])
+    return {**{k: np.asarray(v) for k, v in out.items()}, **g}
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    jobs = [("env_v2", "UR3eEnv2", "gymnasium_env.envs.ur3e_env2", 260, 11, False),
+            ("env_v0", "UR3eEnv", "gymnasium_env.envs.ur3e_env", 260, 12, False),
+            ("env_indirect", "ImitationEnvIndirect", "gymnasium_env.envs.imitation_env_indirect", 260, 13, False)]
+    for name, cls, module, steps, seed, direct in jobs:
+        rec = env_episode(cls, module, steps, seed, direct)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
+        print(name, "steps", len(rec["reward"]), "sum reward %.6f" % rec["reward"].sum(), "grasp max", rec["obs"][:, 23 if rec["obs"].shape[1] == 24 else 9].max(),
+              "term", rec["terminated"].any(), "trunc", rec["truncated"].any())
+    cv = controller_vectors(5)
+    np.savez_compressed(os.path.join(OUT, "controllers.npz"), **cv)
+    print("controllers", cv["u_task"].shape, cv["u_joint"].shape)
+    # the one golden vector the reference itself records: tcp site position at keyframe 'down' (assets/main.xml:415)
+    import mujoco
+    m, d = uu.load_model("assets/main.xml"); uu.reset(m, d, "down")
+    print("tcp@down", uu.get_site_xpos(m, d, "tcp"), "rotvec", uu.get_site_xrotvec(m, d, "tcp"))
+
+
+if __name__ == "__main__":
+    main()
