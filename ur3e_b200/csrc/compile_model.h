@@ -74,7 +74,8 @@ DevModel<Real> compile_model(const HostModel& h) {
     cp(m.dof_range[d], h.D("jnt_range"), 2 * j, 2); m.dof_margin[d] = (Real)h.D("jnt_margin")[j];
     cp(m.dof_lim_solref[d], h.D("jnt_solref"), 2 * j, 2); cp(m.dof_lim_solimp[d], h.D("jnt_solimp"), 5 * j, 5);
     cp(m.dof_fl_solref[d], h.D("dof_solref"), 2 * d, 2); cp(m.dof_fl_solimp[d], h.D("dof_solimp"), 5 * d, 5);
-    if (h.D("dof_frictionloss")[d] > 0) m.fl_dof[nfl++] = d;
+    m.dof_flrow[d] = -1;
+    if (h.D("dof_frictionloss")[d] > 0) { m.dof_flrow[d] = nfl; m.fl_dof[nfl++] = d; }
     if (h.D("dof_damping")[d] > 0) damp = 1;
   }
   m.nfl = nfl; m.has_damping = damp;

@@ -52,6 +52,7 @@ struct DevModel {
   Real dof_armature[MAXV], dof_damping[MAXV], dof_frictionloss[MAXV], dof_invw[MAXV], dof_stiffness[MAXV], dof_springref[MAXV];
   Real dof_range[MAXV][2], dof_margin[MAXV], dof_lim_solref[MAXV][2], dof_lim_solimp[MAXV][5], dof_fl_solref[MAXV][2], dof_fl_solimp[MAXV][5];
   int fl_dof[MAXV];  // dofs with frictionloss, in order
+  int dof_flrow[MAXV];  // position of the dof in fl_dof, -1 when it has no friction loss
   // lower-triangular sparsity of M: (i, j) with j ancestor-or-self of i
   int M_i[MAXNM], M_j[MAXNM];
   int tri_ab[(MAXV + 1) * (MAXV + 2) / 2];  // (a << 8 | b), b <= a, row-major lower triangle of the (nv+1)^2 augmented matrix

@@ -17,10 +17,12 @@ struct Dims {
   static constexpr int MAXCON = MAXCON_ > 0 ? MAXCON_ : 1, MAXEFC = MAXEFC_ > 0 ? MAXEFC_ : 1;
   static constexpr bool HAS_CONTACT = MAXCON_ > 0;
   static constexpr int NS = MAXSITE;
+  static constexpr int HS = (NV_ + 1 + 3) / 4 * 4;
+  static constexpr int NGRP = MAXEQ + NPAIR;
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // assets/ur3e_raw.xml
-using DimsGrip = Dims<23, 14, 14, 7, 6, 12, 16, 72>;    // assets/ur3e_2f85.xml
-using DimsMain = Dims<25, 20, 21, 7, 7, 16, 32, 112>;   // assets/main.xml
+using DimsGrip = Dims<23, 14, 14, 7, 6, 12, 16, 64>;    // assets/ur3e_2f85.xml
+using DimsMain = Dims<25, 20, 21, 7, 7, 16, 24, 96>;   // assets/main.xml
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 
@@ -44,19 +46,27 @@ template <typename Real, typename D>
 struct Arena {
   EnvState<Real, D> st;
   Real qacc[D::NV], ctrl[D::NU], act_force[D::NU], obs[32];
-  Real xpos[D::NB][3], xquat[D::NB][4], xmat[D::NB][9], xipos[D::NB][3];
+  Real xpos[D::NB][3];
+  union {   // body frames are dead once the constraint rows exist; the Newton / Euler matrix reuses their storage
+    struct { Real xquat[D::NB][4], xmat[D::NB][9], xipos[D::NB][3]; } k;
+    struct { alignas(16) Real H[D::NV + 1][D::HS]; } n;   // rows padded to a multiple of 4
+  } fr;
+  alignas(16) Real colbuf[2][32];
+  Real dinv[D::NV];
   Real cdof[D::NV][6];
   Real M[D::NV][D::NV];
-  Real H[D::NV + 1][D::NV + 1];
   Real qfrc_smooth[D::NV], qfrc_bias[D::NV], qfrc_constraint[D::NV], grad[D::NV], search[D::NV], Ma[D::NV], Mv[D::NV];
   Real geom_xpos[D::NG][3], geom_xmat[D::NG][9], site_xpos[D::NS][3], site_xmat[D::NS][9], site_velp[D::NS][3];
-  Real con_pos[D::MAXCON][3], con_frame[D::MAXCON][9], con_dist[D::MAXCON], con_mu[D::MAXCON], con_H[D::MAXCON][6];
-  Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_R[D::MAXEFC], efc_force[D::MAXEFC], efc_jar[D::MAXEFC], efc_jv[D::MAXEFC],
-      efc_fl[D::MAXEFC], efc_Dact[D::MAXEFC];
-  int con_pair[D::MAXCON], con_row[D::MAXCON];
-  int efc_type[D::MAXEFC], efc_id[D::MAXEFC];
-  int stage_n[D::NPAIR], stage_off[D::NPAIR];
-  int ncon, nefc, ne, nf, nl, overflow, solver_iter, bad;
+  Real con_pos[D::MAXCON][3], con_dist[D::MAXCON], con_mu[D::MAXCON];
+  union { Real frame[D::MAXCON][9]; Real H[D::MAXCON][6]; } cu;   // contact frames (row assembly) / cone Hessians (solver)
+  Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_force[D::MAXEFC], efc_jar[D::MAXEFC], efc_jv[D::MAXEFC], efc_Dact[D::MAXEFC];
+  uint8_t con_pair[D::MAXCON], con_row[D::MAXCON];
+  uint8_t efc_type[D::MAXEFC], efc_id[D::MAXEFC];
+  // row groups sharing one column set (a connect equality, the joint equality, the contacts of one geom pair)
+  int grp_mask[D::NGRP];
+  uint8_t grp_row0[D::NGRP], grp_nrow[D::NGRP];
+  uint8_t stage_n[D::NPAIR], stage_off[D::NPAIR];
+  int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad;
   union {
     struct { Real cinert[D::NB][10], crb[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6], fbuf[D::NV][6]; } dyn;
     Real stage[D::NPAIR][STAGE_PTS][7];  // pos 3, normal 3, dist
@@ -159,9 +169,9 @@ UR3E_HD void fk_body(const DevModel<Real>& m, Arena<Real, D>& s, int b) {
     }
   } else {
     Real v[3];
-    mat_vec3(v, s.xmat[p], m.body_pos[b]);
+    mat_vec3(v, s.fr.k.xmat[p], m.body_pos[b]);
     for (int k = 0; k < 3; ++k) pos[k] = s.xpos[p][k] + v[k];
-    quat_mul(quat, s.xquat[p], m.body_quat[b]);
+    quat_mul(quat, s.fr.k.xquat[p], m.body_quat[b]);
     if (jk == JK_HINGE) {
       Real R0[9], anchor[3], axis[3], vec[3];
       quat2mat(R0, quat);
@@ -185,19 +195,19 @@ UR3E_HD void fk_body(const DevModel<Real>& m, Arena<Real, D>& s, int b) {
     }
   }
   for (int k = 0; k < 3; ++k) s.xpos[b][k] = pos[k];
-  for (int k = 0; k < 4; ++k) s.xquat[b][k] = quat[k];
-  quat2mat(s.xmat[b], quat);
+  for (int k = 0; k < 4; ++k) s.fr.k.xquat[b][k] = quat[k];
+  quat2mat(s.fr.k.xmat[b], quat);
   Real v[3];
-  mat_vec3(v, s.xmat[b], m.body_ipos[b]);
-  for (int k = 0; k < 3; ++k) s.xipos[b][k] = pos[k] + v[k];
+  mat_vec3(v, s.fr.k.xmat[b], m.body_ipos[b]);
+  for (int k = 0; k < 3; ++k) s.fr.k.xipos[b][k] = pos[k] + v[k];
 }
 
 template <typename Real, typename D>
 UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
   IF_LANE0 {
-    for (int k = 0; k < 3; ++k) { s.xpos[0][k] = 0; s.xipos[0][k] = 0; }
-    s.xquat[0][0] = 1; s.xquat[0][1] = s.xquat[0][2] = s.xquat[0][3] = 0;
-    for (int k = 0; k < 9; ++k) s.xmat[0][k] = (k % 4 == 0) ? Real(1) : Real(0);
+    for (int k = 0; k < 3; ++k) { s.xpos[0][k] = 0; s.fr.k.xipos[0][k] = 0; }
+    s.fr.k.xquat[0][0] = 1; s.fr.k.xquat[0][1] = s.fr.k.xquat[0][2] = s.fr.k.xquat[0][3] = 0;
+    for (int k = 0; k < 9; ++k) s.fr.k.xmat[0][k] = (k % 4 == 0) ? Real(1) : Real(0);
   }
   WARP_SYNC();
   for (int lev = 1; lev < m.nlevel; ++lev) {
@@ -208,14 +218,14 @@ UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
   WARP_FOR(i, m.ngeom + m.nsite) {
     if (i < m.ngeom) {
       int b = m.geom_body[i]; Real v[3], q[4];
-      mat_vec3(v, s.xmat[b], m.geom_pos[i]);
+      mat_vec3(v, s.fr.k.xmat[b], m.geom_pos[i]);
       for (int k = 0; k < 3; ++k) s.geom_xpos[i][k] = s.xpos[b][k] + v[k];
-      quat_mul(q, s.xquat[b], m.geom_quat[i]); quat2mat(s.geom_xmat[i], q);
+      quat_mul(q, s.fr.k.xquat[b], m.geom_quat[i]); quat2mat(s.geom_xmat[i], q);
     } else {
       int j = i - m.ngeom, b = m.site_body[j]; Real v[3], q[4];
-      mat_vec3(v, s.xmat[b], m.site_pos[j]);
+      mat_vec3(v, s.fr.k.xmat[b], m.site_pos[j]);
       for (int k = 0; k < 3; ++k) s.site_xpos[j][k] = s.xpos[b][k] + v[k];
-      quat_mul(q, s.xquat[b], m.site_quat[j]); quat2mat(s.site_xmat[j], q);
+      quat_mul(q, s.fr.k.xquat[b], m.site_quat[j]); quat2mat(s.site_xmat[j], q);
     }
   }
   WARP_SYNC();
@@ -232,8 +242,8 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
     if (b == 0 || m.body_lastdof[b] < 0) { for (int k = 0; k < 10; ++k) ci[k] = 0; for (int k = 0; k < 6; ++k) y.cvel[b][k] = 0; }
     else {
       const Real* ref = s.xpos[m.body_root[b]];
-      Real dif[3] = {s.xipos[b][0] - ref[0], s.xipos[b][1] - ref[1], s.xipos[b][2] - ref[2]};
-      Real q[4], R[9]; quat_mul(q, s.xquat[b], m.body_iquat[b]); quat2mat(R, q);
+      Real dif[3] = {s.fr.k.xipos[b][0] - ref[0], s.fr.k.xipos[b][1] - ref[1], s.fr.k.xipos[b][2] - ref[2]};
+      Real q[4], R[9]; quat_mul(q, s.fr.k.xquat[b], m.body_iquat[b]); quat2mat(R, q);
       const Real* in = m.body_inertia[b]; Real mass = m.body_mass[b];
       Real t00 = 0, t11 = 0, t22 = 0, t01 = 0, t02 = 0, t12 = 0;
       for (int k = 0; k < 3; ++k) {
@@ -469,11 +479,11 @@ UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
       }
       int keep = 0;   // MuJoCo keeps a contact only when dist < margin
       for (int c = 0; c < n; ++c) if (s.u.stage[p][c][6] < margin) { if (keep != c) for (int k = 0; k < 7; ++k) s.u.stage[p][keep][k] = s.u.stage[p][c][k]; ++keep; }
-      s.stage_n[p] = keep;
+      s.stage_n[p] = (uint8_t)keep;
     }
     WARP_SYNC();
     int total = 0;
-    for (int p = 0; p < m.npair; ++p) { int n = s.stage_n[p]; IF_LANE0 s.stage_off[p] = total; total += n; }
+    for (int p = 0; p < m.npair; ++p) { int n = s.stage_n[p]; IF_LANE0 s.stage_off[p] = (uint8_t)total; total += n; }
     int ncon = total > D::MAXCON ? D::MAXCON : total;
     IF_LANE0 { s.ncon = ncon; if (total > D::MAXCON) s.overflow |= 1; }
     WARP_SYNC();
@@ -482,9 +492,9 @@ UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
       int o = s.stage_off[p] + c;
       if (c < s.stage_n[p] && o < D::MAXCON) {
         const Real* src = s.u.stage[p][c];
-        for (int k = 0; k < 3; ++k) { s.con_pos[o][k] = src[k]; s.con_frame[o][k] = src[3 + k]; }
-        s.con_dist[o] = src[6]; s.con_pair[o] = p;
-        make_frame(s.con_frame[o]);
+        for (int k = 0; k < 3; ++k) { s.con_pos[o][k] = src[k]; s.cu.frame[o][k] = src[3 + k]; }
+        s.con_dist[o] = src[6]; s.con_pair[o] = (uint8_t)p;
+        make_frame(s.cu.frame[o]);
       }
     }
     WARP_SYNC();
@@ -546,23 +556,46 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   int ncon = s.ncon;
   if (base_c + 3 * ncon > D::MAXEFC) { ncon = (D::MAXEFC - base_c) / 3; if (ncon < 0) ncon = 0; IF_LANE0 { s.overflow |= 2; s.ncon = ncon; } }
   int nefc = base_c + 3 * ncon; if (nefc > D::MAXEFC) nefc = D::MAXEFC;
-  IF_LANE0 { s.ne = ne; s.nf = nf; s.nl = nl; s.nefc = nefc; }
+  // row groups: rows that share one column set (used by the Hessian assembly)
+  int ngrp = 0;
+  {
+    int row = 0;
+    for (int e = 0; e < m.neq; ++e) {
+      const bool con = m.eq_kind[e] == EK_CONNECT;
+      const int mask = con ? (int)(m.body_dofmask[m.eq_o1[e]] | m.body_dofmask[m.eq_o2[e]]) : ((1 << m.eq_o1[e]) | (m.eq_o2[e] >= 0 ? (1 << m.eq_o2[e]) : 0));
+      IF_LANE0 { s.grp_row0[ngrp] = (uint8_t)row; s.grp_nrow[ngrp] = con ? 3 : 1; s.grp_mask[ngrp] = mask; }
+      ++ngrp; row += con ? 3 : 1;
+    }
+    if constexpr (D::HAS_CONTACT) {
+      int prev = -1;
+      for (int c = 0; c < ncon; ++c) {
+        const int p = s.con_pair[c];
+        if (p != prev) {
+          const int mask = (int)(m.body_dofmask[m.geom_body[m.pair_g1[p]]] ^ m.body_dofmask[m.geom_body[m.pair_g2[p]]]);
+          IF_LANE0 { s.grp_row0[ngrp] = (uint8_t)(base_c + 3 * c); s.grp_nrow[ngrp] = 0; s.grp_mask[ngrp] = mask; }
+          ++ngrp; prev = p;
+        }
+        IF_LANE0 s.grp_nrow[ngrp - 1] += 3;
+      }
+    }
+  }
+  IF_LANE0 { s.ne = ne; s.nf = nf; s.nl = nl; s.nefc = nefc; s.ngrp = ngrp; s.lim_lo = mlo; s.lim_hi = mhi; }
   WARP_FOR(i, nefc * nv) (&s.u.efc_J[0][0])[i] = 0;
   WARP_SYNC();
-  // equality rows; efc_aref temporarily holds pos, efc_R holds margin
+  // equality rows; efc_aref temporarily holds pos, efc_jv holds margin
   {
     int row = 0;
     for (int e = 0; e < m.neq; ++e) {
       if (m.eq_kind[e] == EK_CONNECT) {
         int b1 = m.eq_o1[e], b2 = m.eq_o2[e];
         Real a1[3], a2[3], v[3];
-        mat_vec3(v, s.xmat[b1], m.eq_data[e]); for (int k = 0; k < 3; ++k) a1[k] = s.xpos[b1][k] + v[k];
-        mat_vec3(v, s.xmat[b2], m.eq_data[e] + 3); for (int k = 0; k < 3; ++k) a2[k] = s.xpos[b2][k] + v[k];
+        mat_vec3(v, s.fr.k.xmat[b1], m.eq_data[e]); for (int k = 0; k < 3; ++k) a1[k] = s.xpos[b1][k] + v[k];
+        mat_vec3(v, s.fr.k.xmat[b2], m.eq_data[e] + 3); for (int k = 0; k < 3; ++k) a2[k] = s.xpos[b2][k] + v[k];
         WARP_FOR(d, nv) {
           Real j1[3], j2[3]; jac_col(m, s, d, a1, b1, j1); jac_col(m, s, d, a2, b2, j2);
           for (int r = 0; r < 3; ++r) s.u.efc_J[row + r][d] = j1[r] - j2[r];
         }
-        WARP_FOR(r, 3) { s.efc_aref[row + r] = a1[r] - a2[r]; s.efc_R[row + r] = 0; s.efc_type[row + r] = ROW_EQ; s.efc_id[row + r] = e; s.efc_fl[row + r] = 0; }
+        WARP_FOR(r, 3) { s.efc_aref[row + r] = a1[r] - a2[r]; s.efc_jv[row + r] = 0; s.efc_type[row + r] = ROW_EQ; s.efc_id[row + r] = (uint8_t)e; }
         row += 3;
       } else {
         IF_LANE0 {
@@ -576,7 +609,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
             s.u.efc_J[row][d2] = -deriv;
           } else pos = p1 - c[0];
           s.u.efc_J[row][d1] = 1;
-          s.efc_aref[row] = pos; s.efc_R[row] = 0; s.efc_type[row] = ROW_EQ; s.efc_id[row] = e; s.efc_fl[row] = 0;
+          s.efc_aref[row] = pos; s.efc_jv[row] = 0; s.efc_type[row] = ROW_EQ; s.efc_id[row] = (uint8_t)e;
         }
         row += 1;
       }
@@ -584,7 +617,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   }
   WARP_FOR(k, nf) {
     int d = m.fl_dof[k], r = ne + k;
-    s.u.efc_J[r][d] = 1; s.efc_aref[r] = 0; s.efc_R[r] = 0; s.efc_type[r] = ROW_FRICTION; s.efc_id[r] = d; s.efc_fl[r] = m.dof_frictionloss[d];
+    s.u.efc_J[r][d] = 1; s.efc_aref[r] = 0; s.efc_jv[r] = 0; s.efc_type[r] = ROW_FRICTION; s.efc_id[r] = (uint8_t)d;
   }
   WARP_FOR(i, 2 * nv) {
     int d = i >> 1, k = i & 1;
@@ -596,7 +629,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
         Real q = s.st.qpos[m.dof_qadr[d]];
         s.u.efc_J[r][d] = k == 0 ? Real(1) : Real(-1);
         s.efc_aref[r] = k == 0 ? q - m.dof_range[d][0] : m.dof_range[d][1] - q;
-        s.efc_R[r] = m.dof_margin[d]; s.efc_type[r] = ROW_LIMIT; s.efc_id[r] = d; s.efc_fl[r] = 0;
+        s.efc_jv[r] = m.dof_margin[d]; s.efc_type[r] = ROW_LIMIT; s.efc_id[r] = (uint8_t)d;
       }
     }
   }
@@ -607,20 +640,20 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
       Real j1[3], j2[3]; jac_col(m, s, d, s.con_pos[c], b1, j1); jac_col(m, s, d, s.con_pos[c], b2, j2);
       Real dj[3] = {j2[0] - j1[0], j2[1] - j1[1], j2[2] - j1[2]};
       int r0 = base_c + 3 * c;
-      for (int r = 0; r < 3; ++r) s.u.efc_J[r0 + r][d] = dot3(s.con_frame[c] + 3 * r, dj);
+      for (int r = 0; r < 3; ++r) s.u.efc_J[r0 + r][d] = dot3(s.cu.frame[c] + 3 * r, dj);
     }
     WARP_FOR(i, 3 * ncon) {
       int c = i / 3, r = i - 3 * c, row = base_c + i, p = s.con_pair[c];
-      s.efc_aref[row] = r == 0 ? s.con_dist[c] : Real(0); s.efc_R[row] = r == 0 ? m.pair_includemargin[p] : Real(0);
-      s.efc_type[row] = ROW_CON_N + r; s.efc_id[row] = c; s.efc_fl[row] = 0;
-      if (r == 0) s.con_row[c] = row;
+      s.efc_aref[row] = r == 0 ? s.con_dist[c] : Real(0); s.efc_jv[row] = r == 0 ? m.pair_includemargin[p] : Real(0);
+      s.efc_type[row] = (uint8_t)(ROW_CON_N + r); s.efc_id[row] = (uint8_t)c;
+      if (r == 0) s.con_row[c] = (uint8_t)row;
     }
   }
   WARP_SYNC();
   // impedance, K/B, R, D, aref  (mj_makeImpedance + mj_referenceConstraint)
   WARP_FOR(r, nefc) {
     int t = s.efc_type[r], id = s.efc_id[r];
-    Real pos = s.efc_aref[r], margin = s.efc_R[r];
+    Real pos = s.efc_aref[r], margin = s.efc_jv[r];
     const Real *solref, *solimp; Real diag; bool fric = false;
     if (t == ROW_EQ) { solref = m.eq_solref[id]; solimp = m.eq_solimp[id]; diag = m.eq_invw[id]; }
     else if (t == ROW_FRICTION) { solref = m.dof_fl_solref[id]; solimp = m.dof_fl_solimp[id]; diag = m.dof_invw[id]; fric = true; }
@@ -644,41 +677,70 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
     }
     if (fric) K = 0;
     Real vel = 0; for (int k = 0; k < nv; ++k) vel += s.u.efc_J[r][k] * s.st.qvel[k];
-    s.efc_R[r] = R; s.efc_D[r] = 1 / R;
+    s.efc_D[r] = 1 / R;
     s.efc_aref[r] = -B * vel - K * imp * (pos - margin);
   }
   WARP_SYNC();
 }
 
 // ---------------------------------------------------------------- dense SPD solve on the augmented matrix
-// Factors the leading n x n block of s.H (lower triangle) in place, with row n = rhs: after the call
-// H[n][0..n) = L^-1 rhs.  Then back-substitutes into x (shared memory, length n).
+// Input: lower triangle of s.fr.n.H, rows 0..n-1 = SPD matrix, row n = right-hand side (n == D::NV).
+// Row-per-lane Cholesky held in registers: lane i owns row i; at step k the raw column k is published through a
+// double-buffered 32-entry shared buffer (one __syncwarp per step), every lane applies the rank-1 update to its own
+// row.  After the last step lane n holds y = L^-1 rhs.  L (and 1/diag) go back to shared memory once and every lane
+// runs the back-substitution redundantly in registers (no further synchronisation).  Output x[0..n) in shared memory.
 template <typename Real, typename D>
 UR3E_HD void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
-  for (int j = 0; j < n; ++j) {
-    // column j: rows j..n (row n is the rhs)
-    WARP_FOR(i0, n + 1 - j) {
-      int i = j + i0;
-      Real t = s.H[i][j];
-      for (int k = 0; k < j; ++k) t -= s.H[i][k] * s.H[j][k];
-      s.H[i][j] = t;
+  constexpr int N = D::NV + 1;
+  (void)n;
+  LANE_ARRAY(Real, h, N);
+  WARP_FOR(i, N) {
+    Real* r = LA(h, i);
+#pragma unroll
+    for (int j = 0; j < N; ++j) r[j] = j <= i ? s.fr.n.H[i][j] : Real(0);
+  }
+#pragma unroll
+  for (int k = 0; k < N - 1; ++k) {
+    Real* cb = s.colbuf[k & 1];
+    WARP_FOR(i, N) { if (i >= k) cb[i] = LA(h, i)[k]; }
+    WARP_SYNC();
+    Real d = cb[k];
+    d = d > Num<Real>::minval ? d : Num<Real>::minval;
+    const Real inv = Real(1) / d, rs = Real(1) / Num<Real>::sqrt(d);
+    WARP_FOR(i, N) {
+      Real* r = LA(h, i);
+      if (i > k) {
+        const Real t = r[k] * inv;
+#pragma unroll
+        for (int j = k + 1; j < N; ++j) if (j <= i) r[j] -= t * cb[j];
+        r[k] *= rs;
+      } else if (i == k) r[k] = d * rs;
     }
-    WARP_SYNC();
-    Real djj = s.H[j][j];
-    djj = djj > Num<Real>::minval ? djj : Num<Real>::minval;
-    Real inv = 1 / Num<Real>::sqrt(djj);
-    WARP_SYNC();
-    WARP_FOR(i0, n + 1 - j) { int i = j + i0; s.H[i][j] = i == j ? djj * inv : s.H[i][j] * inv; }
-    WARP_SYNC();
   }
-  WARP_FOR(i, n) x[i] = s.H[n][i];
+  WARP_FOR(i, N) {
+    const Real* r = LA(h, i);
+#pragma unroll
+    for (int j = 0; j < N; ++j) if (j <= i) s.fr.n.H[i][j] = r[j];
+    if (i < N - 1) s.dinv[i] = Real(1) / r[i];
+  }
   WARP_SYNC();
-  for (int k = n - 1; k >= 0; --k) {
-    Real xk = x[k] / s.H[k][k];
-    WARP_SYNC();
-    WARP_FOR(i, k + 1) { if (i == k) x[i] = xk; else x[i] -= s.H[k][i] * xk; }
-    WARP_SYNC();
+  Real y[N - 1];
+#pragma unroll
+  for (int j = 0; j < N - 1; ++j) y[j] = s.fr.n.H[N - 1][j];
+#pragma unroll
+  for (int k = N - 2; k >= 0; --k) {
+    const Real xk = y[k] * s.dinv[k];
+    y[k] = xk;
+#pragma unroll
+    for (int i = 0; i < k; ++i) y[i] -= s.fr.n.H[k][i] * xk;
   }
+  WARP_FOR(i, N - 1) {
+    Real v = 0;
+#pragma unroll
+    for (int j = 0; j < N - 1; ++j) if (j == i) v = y[j];
+    x[i] = v;
+  }
+  WARP_SYNC();
 }
 
 // ---------------------------------------------------------------- Newton solver on the primal problem
@@ -690,7 +752,7 @@ UR3E_HD void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bool 
     Real Dr = s.efc_D[r], x = s.efc_jar[r];
     if (t == ROW_EQ) { s.efc_force[r] = -Dr * x; s.efc_Dact[r] = Dr; }
     else if (t == ROW_FRICTION) {
-      Real f = s.efc_fl[r], rf = s.efc_R[r] * f;
+      Real f = m.dof_frictionloss[s.efc_id[r]], rf = f / Dr;
       if (x <= -rf) { s.efc_force[r] = f; s.efc_Dact[r] = 0; }
       else if (x >= rf) { s.efc_force[r] = -f; s.efc_Dact[r] = 0; }
       else { s.efc_force[r] = -Dr * x; s.efc_Dact[r] = Dr; }
@@ -701,7 +763,7 @@ UR3E_HD void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bool 
       Real mu = s.con_mu[c], f1 = m.pair_friction[p][0], f2 = m.pair_friction[p][1];
       Real U0 = x * mu, U1 = s.efc_jar[r + 1] * f1, U2 = s.efc_jar[r + 2] * f2;
       Real T = Num<Real>::sqrt(U1 * U1 + U2 * U2), N = U0;
-      Real* Hc = s.con_H[c];
+      Real* Hc = s.cu.H[c];
       if (N >= mu * T || (T <= 0 && N >= 0)) {
         for (int j = 0; j < 3; ++j) { s.efc_force[r + j] = 0; s.efc_Dact[r + j] = 0; }
         Hc[0] = -1;   // marker: no cone hessian
@@ -734,7 +796,7 @@ UR3E_HD void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real al
     Real Dr = s.efc_D[r], v = s.efc_jv[r], x = s.efc_jar[r] + alpha * v;
     if (t == ROW_EQ) { p1 += Dr * x * v; p2 += Dr * v * v; }
     else if (t == ROW_FRICTION) {
-      Real f = s.efc_fl[r], rf = s.efc_R[r] * f;
+      Real f = m.dof_frictionloss[s.efc_id[r]], rf = f / Dr;
       if (x <= -rf) p1 -= f * v; else if (x >= rf) p1 += f * v; else { p1 += Dr * x * v; p2 += Dr * v * v; }
     } else if (t == ROW_LIMIT) { if (x < 0) { p1 += Dr * x * v; p2 += Dr * v * v; } }
     else if (t == ROW_CON_N) {
@@ -766,7 +828,7 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
   const int nv = m.nv, nefc = s.nefc;
   if (nefc == 0) {
     // unconstrained: qacc = M^-1 qfrc_smooth
-    WARP_FOR(i, nv * (nv + 1)) { int r = i / nv, c = i - r * nv; s.H[r][c] = r < nv ? s.M[r][c] : s.qfrc_smooth[c]; }
+    WARP_FOR(i, nv * (nv + 1)) { int r = i / nv, c = i - r * nv; s.fr.n.H[r][c] = r < nv ? s.M[r][c] : s.qfrc_smooth[c]; }
     WARP_FOR(d, nv) s.qfrc_constraint[d] = 0;
     WARP_SYNC();
     chol_solve_aug(s, nv, s.qacc);
@@ -794,28 +856,50 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
     gg = warp_sum(gg); gref = warp_sum(gref);
     // converged: MuJoCo's scaled-gradient test, or the gradient is at the rounding floor of its own terms
     if (scale * Num<Real>::sqrt(gg) < opt.tol || gg < opt.rtol * opt.rtol * gref) break;
-    // H = M + J^T diag(Dact) J + cone blocks ; augmented row = -grad
-    WARP_FOR(e, (nv + 1) * (nv + 2) / 2) {
-      int ab = m.tri_ab[e], a = ab >> 8, b = ab & 255;   // (a, b), b <= a, over the (nv+1) x (nv+1) lower triangle
-      if (a == nv) { if (b < nv) s.H[nv][b] = -s.grad[b]; }
-      else {
-        Real h = s.M[a][b];
-        for (int r = 0; r < nefc; ++r) { Real da = s.efc_Dact[r]; if (da != 0) h += da * s.u.efc_J[r][a] * s.u.efc_J[r][b]; }
-        if constexpr (D::HAS_CONTACT) {
-          for (int c = 0; c < s.ncon; ++c) {
-            const Real* Hc = s.con_H[c];
-            if (Hc[0] > 0) {
-              int r = s.con_row[c];
-              Real a0 = s.u.efc_J[r][a], a1 = s.u.efc_J[r + 1][a], a2 = s.u.efc_J[r + 2][a];
-              Real b0 = s.u.efc_J[r][b], b1 = s.u.efc_J[r + 1][b], b2 = s.u.efc_J[r + 2][b];
-              h += Hc[0] * a0 * b0 + Hc[1] * (a0 * b1 + a1 * b0) + Hc[2] * (a0 * b2 + a2 * b0) + Hc[3] * a1 * b1 + Hc[4] * (a1 * b2 + a2 * b1) + Hc[5] * a2 * b2;
+    // H = M + J^T diag(Dact) J + cone blocks ; augmented row = -grad.
+    // phase A: M, the single-column rows (friction loss, limits) and the rhs row
+    {
+      const int ne = s.ne, rl0 = s.ne + s.nf, mlo = s.lim_lo, mhi = s.lim_hi;
+      WARP_FOR(e, (nv + 1) * (nv + 2) / 2) {
+        int ab = m.tri_ab[e], a = ab >> 8, b = ab & 255;   // (a, b), b <= a, over the (nv+1) x (nv+1) lower triangle
+        if (a == nv) { if (b < nv) s.fr.n.H[nv][b] = -s.grad[b]; }
+        else {
+          Real h = s.M[a][b];
+          if (a == b) {
+            int k = m.dof_flrow[a];
+            if (k >= 0) h += s.efc_Dact[ne + k];
+            if (((mlo | mhi) >> a) & 1) {
+              int below = (1 << a) - 1, r = rl0 + popcount32(mlo & below) + popcount32(mhi & below);
+              if ((mlo >> a) & 1) { if (r < D::MAXEFC) h += s.efc_Dact[r]; ++r; }
+              if ((mhi >> a) & 1) { if (r < D::MAXEFC) h += s.efc_Dact[r]; }
             }
           }
+          s.fr.n.H[a][b] = h;
         }
-        s.H[a][b] = h;
       }
+      WARP_SYNC();
     }
-    WARP_SYNC();
+    // phase B: one pass per row group over the lower triangle of its own column set
+    for (int g = 0; g < s.ngrp; ++g) {
+      const int r0 = s.grp_row0[g], r1 = r0 + s.grp_nrow[g], mask = s.grp_mask[g], kc = popcount32(mask);
+      const bool contact = s.efc_type[r0] >= ROW_CON_N;
+      WARP_FOR(e, kc * (kc + 1) / 2) {
+        int pq = m.tri_ab[e], a = nth_set_bit(mask, pq >> 8), b = nth_set_bit(mask, pq & 255);
+        Real h = 0;
+        if (!contact) { for (int r = r0; r < r1; ++r) h += s.efc_Dact[r] * s.u.efc_J[r][a] * s.u.efc_J[r][b]; }
+        else {
+          for (int r = r0; r < r1 && r + 2 < D::MAXEFC; r += 3) {
+            Real a0 = s.u.efc_J[r][a], a1 = s.u.efc_J[r + 1][a], a2 = s.u.efc_J[r + 2][a];
+            Real b0 = s.u.efc_J[r][b], b1 = s.u.efc_J[r + 1][b], b2 = s.u.efc_J[r + 2][b];
+            const Real* Hc = s.cu.H[s.efc_id[r]];
+            if (Hc[0] > 0) h += Hc[0] * a0 * b0 + Hc[1] * (a0 * b1 + a1 * b0) + Hc[2] * (a0 * b2 + a2 * b0) + Hc[3] * a1 * b1 + Hc[4] * (a1 * b2 + a2 * b1) + Hc[5] * a2 * b2;
+            else h += s.efc_Dact[r] * a0 * b0 + s.efc_Dact[r + 1] * a1 * b1 + s.efc_Dact[r + 2] * a2 * b2;
+          }
+        }
+        s.fr.n.H[a][b] += h;
+      }
+      WARP_SYNC();
+    }
     chol_solve_aug(s, nv, s.search);
     // Mv, jv, and the quadratic (Gauss) part of the line cost
     WARP_FOR(i, nv + nefc) {
@@ -882,7 +966,7 @@ UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
     // (M + h diag(damping)) a = qfrc_smooth + qfrc_constraint   
     WARP_FOR(i, nv * (nv + 1)) {
       int r = i / nv, c = i - r * nv;
-      s.H[r][c] = r < nv ? s.M[r][c] + (r == c ? h * m.dof_damping[r] : Real(0)) : s.qfrc_smooth[c] + s.qfrc_constraint[c];
+      s.fr.n.H[r][c] = r < nv ? s.M[r][c] + (r == c ? h * m.dof_damping[r] : Real(0)) : s.qfrc_smooth[c] + s.qfrc_constraint[c];
     }
     WARP_SYNC();
     chol_solve_aug(s, nv, s.search);

@@ -26,6 +26,9 @@
 #define WARP_SYNC() __syncwarp()
 #define IF_LANE0 if (UR3E_LANE == 0)
 #define UR3E_LDG(x) __ldg(&(x))
+// per-lane private array (registers); the host build keeps one copy per emulated lane
+#define LANE_ARRAY(T, name, N) T name[N]
+#define LA(name, lane) name
 namespace ur3e {
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll
@@ -39,6 +42,8 @@ template <typename T> __device__ __forceinline__ T warp_max(T v) {
 }
 __device__ __forceinline__ int warp_or(int v) { return (int)__reduce_or_sync(0xffffffffu, (unsigned)v); }
 __device__ __forceinline__ int popcount32(int v) { return __popc((unsigned)v); }
+// index of the n-th (0-based) set bit of v
+__device__ __forceinline__ int nth_set_bit(int v, int n) { return (int)__fns((unsigned)v, 0u, n + 1); }
 }  // namespace ur3e
 #else
 #define UR3E_LANE 0
@@ -46,10 +51,13 @@ __device__ __forceinline__ int popcount32(int v) { return __popc((unsigned)v); }
 #define WARP_SYNC() ((void)0)
 #define IF_LANE0
 #define UR3E_LDG(x) (x)
+#define LANE_ARRAY(T, name, N) T name[32][N]
+#define LA(name, lane) name[lane]
 namespace ur3e {
 template <typename T> inline T warp_sum(T v) { return v; }
 template <typename T> inline T warp_max(T v) { return v; }
 inline int warp_or(int v) { return v; }
 inline int popcount32(int v) { return __builtin_popcount((unsigned)v); }
+inline int nth_set_bit(int v, int n) { for (int b = 0; b < 32; ++b) if ((v >> b) & 1) { if (n == 0) return b; --n; } return 32; }
 }  // namespace ur3e
 #endif
