@@ -28,17 +28,11 @@ struct KArgs {
 };
 
 template <typename Real, typename D> __host__ __device__ constexpr size_t arena_stride() { return (sizeof(Arena<Real, D>) + 15) / 16 * 16; }
-// warps (environments) per block: the value in {1,2,4} that fits most warps into the 228 KB of an SM (1 KB is reserved per block)
+// warps (environments) per block: as many as fit one SM's shared memory (<= 16); the block's warps advance through the
+// substep phases together (block barriers in forward()), so one block per SM shares each phase's code in the I-cache.
 template <typename Real, typename D> __host__ __device__ constexpr int warps_per_block() {
-  int best = 1, best_w = 0;
-  for (int w = 4; w >= 1; w >>= 1) {
-    size_t per_block = arena_stride<Real, D>() * w + 1024;
-    if (arena_stride<Real, D>() * w > 232448) continue;
-    int warps = (int)(233472 / per_block) * w;
-    if (warps > 64) warps = 64;
-    if (warps > best_w) { best_w = warps; best = w; }
-  }
-  return best;
+  int w = (int)((232448 - 1024) / arena_stride<Real, D>());
+  return w > 16 ? 16 : (w < 1 ? 1 : w);
 }
 constexpr int DBG_DOUBLES = MAXV * MAXV + 3 * MAXV + 8 + 4 * MAXCON + CACHE_SIZE;
 
@@ -49,7 +43,9 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
   const int warp = threadIdx.x >> 5;
   long long e = (long long)blockIdx.x * WPB + warp;
   if (a.op == OP_DEBUG) { if (blockIdx.x != 0 || warp != 0) return; e = a.dbg_env; }
-  if (e >= a.n) return;
+  // OP_STEP uses block barriers: a warp past the end keeps running on the last environment and simply does not store
+  const bool live = e < a.n;
+  if (!live) { if (a.op != OP_STEP) return; e = a.n - 1; }
   Arena<Real, D>& s = *reinterpret_cast<Arena<Real, D>*>(reinterpret_cast<unsigned char*>(smem_raw) + warp * arena_stride<Real, D>());
   const DevModel<Real>& m = *a.m;
   const EnvCfg<Real>& c = a.c;
@@ -64,12 +60,13 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
   if (a.op == OP_STEP) {
     StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim);
     const int done = r.terminated | r.truncated;
-    if (done && a.final_obs) { WARP_FOR(i, od) a.final_obs[e * od + i] = s.obs[i]; }
+    if (done && a.final_obs && live) { WARP_FOR(i, od) a.final_obs[e * od + i] = s.obs[i]; }
     if (done && c.auto_reset) {
       env_reset(m, c, s, a.opt, a.seed, a.env_base + (unsigned long long)e);
       ContactFlags cf = contact_flags(m, c, s);
       write_obs(m, c, s, cf);
     }
+    if (!live) return;
     WARP_FOR(i, od) a.obs[e * od + i] = s.obs[i];
     IF_LANE0 { a.rew[e] = r.reward; a.term[e] = (uint8_t)r.terminated; a.trunc[e] = (uint8_t)r.truncated; }
   } else if (a.op == OP_RESET) {

@@ -17,7 +17,7 @@ struct Dims {
   static constexpr int MAXCON = MAXCON_ > 0 ? MAXCON_ : 1, MAXEFC = MAXEFC_ > 0 ? MAXEFC_ : 1;
   static constexpr bool HAS_CONTACT = MAXCON_ > 0;
   static constexpr int NS = MAXSITE;
-  static constexpr int HS = (NV_ + 1 + 3) / 4 * 4;
+  static constexpr int HS = ((NV_ + 1) | 1);   // odd row stride: one row per lane is conflict-free
   static constexpr int NGRP = MAXEQ + NPAIR;
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // assets/ur3e_raw.xml
@@ -203,7 +203,7 @@ UR3E_HD void fk_body(const DevModel<Real>& m, Arena<Real, D>& s, int b) {
 }
 
 template <typename Real, typename D>
-UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_PHASE void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
   IF_LANE0 {
     for (int k = 0; k < 3; ++k) { s.xpos[0][k] = 0; s.fr.k.xipos[0][k] = 0; }
     s.fr.k.xquat[0][0] = 1; s.fr.k.xquat[0][1] = s.fr.k.xquat[0][2] = s.fr.k.xquat[0][3] = 0;
@@ -233,7 +233,7 @@ UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
 
 // ---------------------------------------------------------------- CRBA + RNE
 template <typename Real, typename D>
-UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_PHASE void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nb = m.nbody, nv = m.nv;
   auto& y = s.u.dyn;
   // body inertias about the tree reference point + body velocities (sum over the dof chain)
@@ -349,7 +349,7 @@ template <typename Real> UR3E_HD void make_frame(Real* f) {
 }
 
 template <typename Real>
-UR3E_HD int plane_box(const Real* ppos, const Real* pmat, const Real* bpos, const Real* bmat, const Real* size, Real margin, Real (*out)[7]) {
+UR3E_PHASE int plane_box(const Real* ppos, const Real* pmat, const Real* bpos, const Real* bmat, const Real* size, Real margin, Real (*out)[7]) {
   Real n[3] = {pmat[2], pmat[5], pmat[8]};
   Real dif[3] = {bpos[0] - ppos[0], bpos[1] - ppos[1], bpos[2] - ppos[2]};
   Real cd = dot3(dif, n);
@@ -383,7 +383,7 @@ UR3E_HD int clip_poly(Real* px, Real* py, int n, Real a, Real b, Real c) {
 
 // box-box manifold; same rules as the oracle's box_box (oracle/ur3e_oracle.c), normal from box 1 to box 2
 template <typename Real>
-UR3E_HD int box_box(const Real* p1, const Real* R1, const Real* s1, const Real* p2, const Real* R2, const Real* s2, Real margin, Real (*out)[7]) {
+UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Real* p2, const Real* R2, const Real* s2, Real margin, Real (*out)[7]) {
   Real d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, A1[3][3], A2[3][3];
   for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) { A1[i][k] = R1[3 * k + i]; A2[i][k] = R2[3 * k + i]; }
   Real AC[3][3];
@@ -461,7 +461,7 @@ UR3E_HD int box_box(const Real* p1, const Real* R1, const Real* s1, const Real* 
 }
 
 template <typename Real, typename D>
-UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_PHASE void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
   if constexpr (!D::HAS_CONTACT) { s.ncon = 0; return; }
   else {
     WARP_FOR(p, m.npair) {
@@ -536,7 +536,7 @@ template <typename Real> UR3E_HD void kb_params(const Real* solref, const Real* 
 }
 
 template <typename Real, typename D>
-UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nv = m.nv;
   // row budget: equality, friction loss (static), limits (dynamic), contacts (3 rows each)
   int ne = 0;
@@ -684,69 +684,53 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
 }
 
 // ---------------------------------------------------------------- dense SPD solve on the augmented matrix
-// Input: lower triangle of s.fr.n.H, rows 0..n-1 = SPD matrix, row n = right-hand side (n == D::NV).
-// Row-per-lane Cholesky held in registers: lane i owns row i; at step k the raw column k is published through a
-// double-buffered 32-entry shared buffer (one __syncwarp per step), every lane applies the rank-1 update to its own
-// row.  After the last step lane n holds y = L^-1 rhs.  L (and 1/diag) go back to shared memory once and every lane
-// runs the back-substitution redundantly in registers (no further synchronisation).  Output x[0..n) in shared memory.
+// Input: lower triangle of s.fr.n.H, rows 0..n-1 = SPD matrix, row n = right-hand side.  Output x[0..n) (shared memory).
+// Right-looking Cholesky with one row per lane: at step k lane i (> k) scales its entry of column k and applies the
+// rank-1 update to its own row, reading the raw column k as warp-wide broadcasts; one __syncwarp per step.  Loops are
+// deliberately kept rolled: the step's code has to stay resident in the SM's 32 KB instruction cache (profiles/r1_summary.md).
+// The right-hand side rides along as row n, so after the last step it holds y = L^-1 rhs; the back-substitution then
+// runs column by column with the 1/diagonal saved during the factorisation.
 template <typename Real, typename D>
-UR3E_HD void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
-  constexpr int N = D::NV + 1;
-  (void)n;
-  LANE_ARRAY(Real, h, N);
-  WARP_FOR(i, N) {
-    Real* r = LA(h, i);
-#pragma unroll
-    for (int j = 0; j < N; ++j) r[j] = j <= i ? s.fr.n.H[i][j] : Real(0);
-  }
-#pragma unroll
-  for (int k = 0; k < N - 1; ++k) {
-    Real* cb = s.colbuf[k & 1];
-    WARP_FOR(i, N) { if (i >= k) cb[i] = LA(h, i)[k]; }
-    WARP_SYNC();
-    Real d = cb[k];
+UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
+  const int N = n + 1;
+#pragma unroll 1
+  for (int k = 0; k < n; ++k) {
+    Real d = s.fr.n.H[k][k];
     d = d > Num<Real>::minval ? d : Num<Real>::minval;
-    const Real inv = Real(1) / d, rs = Real(1) / Num<Real>::sqrt(d);
+    const Real inv = Real(1) / d;
     WARP_FOR(i, N) {
-      Real* r = LA(h, i);
       if (i > k) {
-        const Real t = r[k] * inv;
-#pragma unroll
-        for (int j = k + 1; j < N; ++j) if (j <= i) r[j] -= t * cb[j];
-        r[k] *= rs;
-      } else if (i == k) r[k] = d * rs;
+        Real* row = s.fr.n.H[i];
+        const Real t = row[k] * inv;
+#pragma unroll 1
+        for (int j = k + 1; j <= i; ++j) row[j] -= t * s.fr.n.H[j][k];
+      }
     }
+    WARP_SYNC();
   }
-  WARP_FOR(i, N) {
-    const Real* r = LA(h, i);
-#pragma unroll
-    for (int j = 0; j < N; ++j) if (j <= i) s.fr.n.H[i][j] = r[j];
-    if (i < N - 1) s.dinv[i] = Real(1) / r[i];
+  // scale: L[i][k] = raw[i][k] / sqrt(d_k); keep 1/L_kk; y = row n
+  WARP_FOR(k, n) {
+    Real d = s.fr.n.H[k][k];
+    d = d > Num<Real>::minval ? d : Num<Real>::minval;
+    const Real rs = Real(1) / Num<Real>::sqrt(d);
+    s.dinv[k] = rs;                       // 1 / L_kk
+    s.colbuf[0][k] = s.fr.n.H[n][k] * rs;  // y_k
   }
   WARP_SYNC();
-  Real y[N - 1];
-#pragma unroll
-  for (int j = 0; j < N - 1; ++j) y[j] = s.fr.n.H[N - 1][j];
-#pragma unroll
-  for (int k = N - 2; k >= 0; --k) {
+  // back-substitution L^T x = y with L[k][i] = raw[k][i] * dinv[i]; y lives in colbuf so that x is only ever written
+  Real* y = s.colbuf[0];
+#pragma unroll 1
+  for (int k = n - 1; k >= 0; --k) {
     const Real xk = y[k] * s.dinv[k];
-    y[k] = xk;
-#pragma unroll
-    for (int i = 0; i < k; ++i) y[i] -= s.fr.n.H[k][i] * xk;
+    WARP_FOR(i, k + 1) { if (i == k) x[i] = xk; else y[i] -= s.fr.n.H[k][i] * s.dinv[i] * xk; }
+    WARP_SYNC();
   }
-  WARP_FOR(i, N - 1) {
-    Real v = 0;
-#pragma unroll
-    for (int j = 0; j < N - 1; ++j) if (j == i) v = y[j];
-    x[i] = v;
-  }
-  WARP_SYNC();
 }
 
 // ---------------------------------------------------------------- Newton solver on the primal problem
 // per-row cost derivative bookkeeping; cone contacts are processed by the lane that owns their normal row
 template <typename Real, typename D>
-UR3E_HD void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bool want_hess) {
+UR3E_PHASE void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bool want_hess) {
   WARP_FOR(r, s.nefc) {
     int t = s.efc_type[r];
     Real Dr = s.efc_D[r], x = s.efc_jar[r];
@@ -789,7 +773,7 @@ UR3E_HD void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bool 
 
 // derivative / curvature of the cost along qacc + alpha * search (constraint part)
 template <typename Real, typename D>
-UR3E_HD void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real alpha, Real g1, Real g2, Real* dphi, Real* ddphi) {
+UR3E_PHASE void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real alpha, Real g1, Real g2, Real* dphi, Real* ddphi) {
   Real p1 = 0, p2 = 0;
   WARP_FOR(r, s.nefc) {
     int t = s.efc_type[r];
@@ -824,7 +808,7 @@ UR3E_HD void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real al
 template <typename Real> struct SolverOpts { int max_iter; int max_ls; Real tol; Real ls_tol; Real rtol; };
 
 template <typename Real, typename D>
-UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
+UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
   const int nv = m.nv, nefc = s.nefc;
   if (nefc == 0) {
     // unconstrained: qacc = M^-1 qfrc_smooth
@@ -941,15 +925,25 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
 
 // ---------------------------------------------------------------- one mj_step
 template <typename Real, typename D>
-UR3E_HD void forward(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, bool with_solver) {
+UR3E_PHASE void forward(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, bool with_solver, bool aligned = false) {
+  // `aligned`: every warp of the block is on this path (the regular substep), so block-wide barriers keep the warps in the
+  // same phase and they share its code in the SM's instruction cache; all other callers (reset, set_state, redo after a
+  // bad qacc) are warp-divergent and must not touch the barrier.
   kinematics(m, s);
+  if (aligned) BLOCK_SYNC();
   dynamics(m, s);
+  if (aligned) BLOCK_SYNC();
   collision(m, s);
-  if (with_solver) { make_constraint(m, s); solve(m, s, opt); }
+  if (with_solver) {
+    if (aligned) BLOCK_SYNC();
+    make_constraint(m, s);
+    if (aligned) BLOCK_SYNC();
+    solve(m, s, opt);
+  }
 }
 
 template <typename Real, typename D>
-UR3E_HD void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_PHASE void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
   WARP_FOR(i, m.nq) s.st.qpos[i] = m.qpos0[i];
   WARP_FOR(i, m.nv) { s.st.qvel[i] = 0; s.st.qacc_ws[i] = 0; s.qacc[i] = 0; }
   WARP_FOR(i, m.nu) s.ctrl[i] = 0;
@@ -959,7 +953,7 @@ UR3E_HD void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
 template <typename Real> UR3E_HD int is_bad(Real x) { return !(x == x) || x > Real(1e10) || x < Real(-1e10); }
 
 template <typename Real, typename D>
-UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_PHASE void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nv = m.nv; const Real h = m.timestep;
   Real* qa = s.qacc;
   if (m.has_damping) {
@@ -992,18 +986,18 @@ UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
 
 // returns a warning mask: 1 bad qpos, 2 bad qvel, 4 bad qacc (mj_checkPos/Vel/Acc + autoreset)
 template <typename Real, typename D>
-UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
+UR3E_PHASE int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
   int w = 0;
   WARP_FOR(i, m.nq + m.nv) w |= i < m.nq ? is_bad(s.st.qpos[i]) : 2 * is_bad(s.st.qvel[i - m.nq]);
   w = warp_or(w);
   if (w) reset_data(m, s);
-  forward(m, s, opt, true);
+  forward(m, s, opt, true, true);
   int wa = 0;
   WARP_FOR(i, m.nv) wa |= 4 * is_bad(s.qacc[i]);
   wa = warp_or(wa);
   if (wa) { reset_data(m, s); forward(m, s, opt, true); w |= wa; }
   WARP_FOR(d, m.nv) s.st.qacc_ws[d] = s.qacc[d];
-  WARP_SYNC();
+  BLOCK_SYNC();
   euler(m, s);
   return w;
 }

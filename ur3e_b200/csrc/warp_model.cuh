@@ -15,15 +15,19 @@
 #if defined(__CUDACC__)
 #define UR3E_HD __host__ __device__ __forceinline__
 #define UR3E_D __device__ __forceinline__
+// big phase functions: one out-of-line copy each, so the step's code stays resident in the SM's instruction cache
+#define UR3E_PHASE __host__ __device__ __noinline__
 #else
 #define UR3E_HD inline
 #define UR3E_D inline
+#define UR3E_PHASE inline
 #endif
 
 #if defined(__CUDA_ARCH__)
 #define UR3E_LANE ((int)(threadIdx.x & 31))
 #define WARP_FOR(i, n) for (int i = UR3E_LANE; i < (n); i += 32)
 #define WARP_SYNC() __syncwarp()
+#define BLOCK_SYNC() __syncthreads()
 #define IF_LANE0 if (UR3E_LANE == 0)
 #define UR3E_LDG(x) __ldg(&(x))
 // per-lane private array (registers); the host build keeps one copy per emulated lane
@@ -49,6 +53,7 @@ __device__ __forceinline__ int nth_set_bit(int v, int n) { return (int)__fns((un
 #define UR3E_LANE 0
 #define WARP_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define WARP_SYNC() ((void)0)
+#define BLOCK_SYNC() ((void)0)
 #define IF_LANE0
 #define UR3E_LDG(x) (x)
 #define LANE_ARRAY(T, name, N) T name[32][N]
