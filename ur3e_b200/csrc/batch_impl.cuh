@@ -9,6 +9,10 @@
 #include "compile_model.h"
 #include "env.cuh"
 
+#ifndef UR3E_BLOCKS_PER_SM
+#define UR3E_BLOCKS_PER_SM 2
+#endif
+
 namespace ur3e {
 enum Op { OP_STEP = 0, OP_RESET = 1, OP_SET_STATE = 2, OP_DEBUG = 3 };
 
@@ -31,7 +35,9 @@ template <typename Real, typename D> __host__ __device__ constexpr size_t arena_
 // warps (environments) per block: as many as fit one SM's shared memory (<= 16); the block's warps advance through the
 // substep phases together (block barriers in forward()), so one block per SM shares each phase's code in the I-cache.
 template <typename Real, typename D> __host__ __device__ constexpr int warps_per_block() {
-  int w = (int)((232448 - 1024) / arena_stride<Real, D>());
+  // UR3E_BLOCKS_PER_SM co-resident blocks: while one block waits at a barrier the other keeps the issue slots busy
+  int per_sm = (int)((233472 - 1024 * UR3E_BLOCKS_PER_SM) / arena_stride<Real, D>());
+  int w = per_sm / UR3E_BLOCKS_PER_SM;
   return w > 16 ? 16 : (w < 1 ? 1 : w);
 }
 constexpr int DBG_DOUBLES = MAXV * MAXV + 3 * MAXV + 8 + 4 * MAXCON + CACHE_SIZE;

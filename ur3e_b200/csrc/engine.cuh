@@ -79,6 +79,19 @@ template <typename Real> struct Num;
 template <> struct Num<float> {
   static UR3E_HD float sqrt(float x) { return ::sqrtf(x); }
   static UR3E_HD float sin(float x) { return ::sinf(x); }
+  // branch-free sincos: Cody-Waite reduction by pi/2 + the classic single-precision minimax polynomials (error ~1 ulp for
+  // |x| < 1e4); replaces the library calls whose slow paths dominate the kinematics code size
+  static UR3E_HD void sincos(float x, float* sn, float* cs) {
+    float q = ::rintf(x * 0.636619772f);
+    int n = (int)q;
+    float r = ::fmaf(q, -1.5707963109016418f, x); r = ::fmaf(q, -1.5893254712295857e-8f, r);
+    float r2 = r * r;
+    float sp = r + r * r2 * (-1.6666654611e-1f + r2 * (8.3321608736e-3f + r2 * -1.9515295891e-4f));
+    float cp = 1.0f + r2 * (-0.5f + r2 * (4.166664568298827e-2f + r2 * (-1.388731625493765e-3f + r2 * 2.443315711809948e-5f)));
+    float s0 = (n & 1) ? cp : sp, c0 = (n & 1) ? sp : cp;
+    *sn = (n & 2) ? -s0 : s0;
+    *cs = ((n + 1) & 2) ? -c0 : c0;
+  }
   static UR3E_HD float cos(float x) { return ::cosf(x); }
   static UR3E_HD float atan2(float y, float x) { return ::atan2f(y, x); }
   static UR3E_HD float pow(float x, float y) { return ::powf(x, y); }
@@ -90,6 +103,7 @@ template <> struct Num<float> {
 template <> struct Num<double> {
   static UR3E_HD double sqrt(double x) { return ::sqrt(x); }
   static UR3E_HD double sin(double x) { return ::sin(x); }
+  static UR3E_HD void sincos(double x, double* sn, double* cs) { *sn = ::sin(x); *cs = ::cos(x); }
   static UR3E_HD double cos(double x) { return ::cos(x); }
   static UR3E_HD double atan2(double y, double x) { return ::atan2(y, x); }
   static UR3E_HD double pow(double x, double y) { return ::pow(x, y); }
@@ -178,7 +192,8 @@ UR3E_HD void fk_body(const DevModel<Real>& m, Arena<Real, D>& s, int b) {
       mat_vec3(vec, R0, m.jnt_pos[b]);
       for (int k = 0; k < 3; ++k) anchor[k] = pos[k] + vec[k];
       mat_vec3(axis, R0, m.jnt_axis[b]);
-      Real ang = s.st.qpos[m.body_qadr[b]] - m.jnt_q0[b], sn = Num<Real>::sin(ang * Real(0.5)), cs = Num<Real>::cos(ang * Real(0.5));
+      Real ang = s.st.qpos[m.body_qadr[b]] - m.jnt_q0[b], sn, cs;
+      Num<Real>::sincos(ang * Real(0.5), &sn, &cs);
       Real ql[4] = {cs, m.jnt_axis[b][0] * sn, m.jnt_axis[b][1] * sn, m.jnt_axis[b][2] * sn};
       quat_mul(quat, quat, ql);
       quat_normalize(quat);
@@ -692,37 +707,45 @@ UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
 // runs column by column with the 1/diagonal saved during the factorisation.
 template <typename Real, typename D>
 UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
-  const int N = n + 1;
+  // factor (unscaled): after step k, raw[i][k] = L[i][k] * L[k][k]; exact zeros (block / tree sparsity of M + J^T D J) are skipped
 #pragma unroll 1
-  for (int k = 0; k < n; ++k) {
+  for (int k = 0; k < n - 1; ++k) {
     Real d = s.fr.n.H[k][k];
     d = d > Num<Real>::minval ? d : Num<Real>::minval;
     const Real inv = Real(1) / d;
-    WARP_FOR(i, N) {
+    WARP_FOR(i, n) {
       if (i > k) {
         Real* row = s.fr.n.H[i];
         const Real t = row[k] * inv;
-#pragma unroll 1
-        for (int j = k + 1; j <= i; ++j) row[j] -= t * s.fr.n.H[j][k];
+        if (t != 0) {
+#pragma unroll 4
+          for (int j = k + 1; j <= i; ++j) row[j] -= t * s.fr.n.H[j][k];
+        }
       }
     }
     WARP_SYNC();
   }
-  // scale: L[i][k] = raw[i][k] / sqrt(d_k); keep 1/L_kk; y = row n
+  Real* y = s.colbuf[0];
   WARP_FOR(k, n) {
     Real d = s.fr.n.H[k][k];
     d = d > Num<Real>::minval ? d : Num<Real>::minval;
-    const Real rs = Real(1) / Num<Real>::sqrt(d);
-    s.dinv[k] = rs;                       // 1 / L_kk
-    s.colbuf[0][k] = s.fr.n.H[n][k] * rs;  // y_k
+    s.dinv[k] = Real(1) / Num<Real>::sqrt(d);     // 1 / L_kk
+    y[k] = s.fr.n.H[n][k];                        // right-hand side
   }
   WARP_SYNC();
-  // back-substitution L^T x = y with L[k][i] = raw[k][i] * dinv[i]; y lives in colbuf so that x is only ever written
-  Real* y = s.colbuf[0];
+  // forward substitution L y = b, L[i][k] = raw[i][k] * dinv[k]
+#pragma unroll 1
+  Real* z = s.colbuf[1];   // z = L^-1 b ; written once per entry, so one barrier per step suffices
+  for (int k = 0; k < n; ++k) {
+    const Real dk = s.dinv[k], yk = y[k] * dk;
+    WARP_FOR(i0, n - k) { int i = k + i0; if (i == k) z[i] = yk; else y[i] -= s.fr.n.H[i][k] * dk * yk; }
+    WARP_SYNC();
+  }
+  // back substitution L^T x = z; x is only ever written
 #pragma unroll 1
   for (int k = n - 1; k >= 0; --k) {
-    const Real xk = y[k] * s.dinv[k];
-    WARP_FOR(i, k + 1) { if (i == k) x[i] = xk; else y[i] -= s.fr.n.H[k][i] * s.dinv[i] * xk; }
+    const Real xk = z[k] * s.dinv[k];
+    WARP_FOR(i, k + 1) { if (i == k) x[i] = xk; else z[i] -= s.fr.n.H[k][i] * s.dinv[i] * xk; }
     WARP_SYNC();
   }
 }
@@ -975,7 +998,7 @@ UR3E_PHASE void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
       Real w[3] = {s.st.qvel[d], s.st.qvel[d + 1], s.st.qvel[d + 2]};
       Real n = Num<Real>::sqrt(dot3(w, w)), ang = h * n;
       Real qr[4] = {1, 0, 0, 0};
-      if (n >= Num<Real>::minval && ang != 0) { Real sn = Num<Real>::sin(ang * Real(0.5)) / n; qr[0] = Num<Real>::cos(ang * Real(0.5)); qr[1] = w[0] * sn; qr[2] = w[1] * sn; qr[3] = w[2] * sn; }
+      if (n >= Num<Real>::minval && ang != 0) { Real sn, cs; Num<Real>::sincos(ang * Real(0.5), &sn, &cs); sn /= n; qr[0] = cs; qr[1] = w[0] * sn; qr[2] = w[1] * sn; qr[3] = w[2] * sn; }
       Real qq[4] = {s.st.qpos[q], s.st.qpos[q + 1], s.st.qpos[q + 2], s.st.qpos[q + 3]}, out[4];
       quat_normalize(qq); quat_mul(out, qq, qr);
       for (int k = 0; k < 4; ++k) s.st.qpos[q + k] = out[k];

@@ -21,7 +21,7 @@ template <typename Real> UR3E_HD Real u01(uint32_t x) { return (Real)((double)x 
 // rotvec of R_target * R_site^T  (controller_func.py:30-48, scipy conventions: SURVEY App. C)
 template <typename Real> UR3E_HD void rot_err(const Real* xmat, const Real* rv, Real* err) {
   Real ang = Num<Real>::sqrt(dot3(rv, rv)), q[4] = {1, 0, 0, 0};
-  if (ang > Real(1e-30)) { Real sn = Num<Real>::sin(ang * Real(0.5)) / ang; q[0] = Num<Real>::cos(ang * Real(0.5)); q[1] = rv[0] * sn; q[2] = rv[1] * sn; q[3] = rv[2] * sn; }
+  if (ang > Real(1e-30)) { Real sn, cs; Num<Real>::sincos(ang * Real(0.5), &sn, &cs); sn /= ang; q[0] = cs; q[1] = rv[0] * sn; q[2] = rv[1] * sn; q[3] = rv[2] * sn; }
   Real Rt[9], E[9]; quat2mat(Rt, q);
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) E[3 * i + j] = Rt[3 * i] * xmat[3 * j] + Rt[3 * i + 1] * xmat[3 * j + 1] + Rt[3 * i + 2] * xmat[3 * j + 2];
   Real tr = E[0] + E[4] + E[8], w, x, y, z;
