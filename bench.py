@@ -205,6 +205,7 @@ def main():
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = float(sum(step_ms))
     launches = batch.launch_count - launches0
+    ki = batch.kernel_info()
     st = batch.stats_dict(reset=True)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:

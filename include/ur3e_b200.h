@@ -92,6 +92,9 @@ int ur3e_batch_debug_forward(ur3e_batch* b, int64_t env, double* M_nvnv, double*
 /* kernels launched by this batch so far; bytes of shared memory per environment; environments resident per SM */
 int64_t ur3e_batch_launch_count(const ur3e_batch* b);
 int ur3e_batch_kernel_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t* warps_per_block, int32_t* blocks_per_sm, int32_t* regs_per_thread);
+/* two-tier stepping of the float32 main.xml batch: out8 = lite arena bytes, lite warps/block, lite blocks/SM,
+ * lite registers, lite-tier steps, full-only steps, environments handed to the full tier at the last observed step, 0; all zero when the batch has a single size class */
+int ur3e_batch_tier_info(const ur3e_batch* b, int64_t* out8);
 /* bytes of the persistent per-environment record in HBM (read + written once per step) */
 int ur3e_batch_state_bytes(const ur3e_batch* b);
 

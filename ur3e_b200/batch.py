@@ -125,8 +125,14 @@ class SimBatch:
     def kernel_info(self):
         v = [C.c_int32() for _ in range(4)]
         _lib.check(self._L.ur3e_batch_kernel_info(self.ptr, *[C.byref(x) for x in v]), "ur3e_batch_kernel_info")
-        return dict(arena_bytes=v[0].value, warps_per_block=v[1].value, blocks_per_sm=v[2].value, regs_per_thread=v[3].value,
-                    state_bytes=int(self._L.ur3e_batch_state_bytes(self.ptr)))
+        t = (C.c_int64 * 8)()
+        _lib.check(self._L.ur3e_batch_tier_info(self.ptr, t), "ur3e_batch_tier_info")
+        d = dict(arena_bytes=v[0].value, warps_per_block=v[1].value, blocks_per_sm=v[2].value, regs_per_thread=v[3].value,
+                 state_bytes=int(self._L.ur3e_batch_state_bytes(self.ptr)))
+        if t[0]:
+            d["lite"] = dict(arena_bytes=int(t[0]), warps_per_block=int(t[1]), blocks_per_sm=int(t[2]), regs_per_thread=int(t[3]),
+                             lite_tier_steps=int(t[4]), full_only_steps=int(t[5]), last_overflow_envs=int(t[6]))
+        return d
 
     def close(self):
         if getattr(self, "ptr", None):

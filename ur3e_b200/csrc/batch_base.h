@@ -28,7 +28,10 @@ struct BatchBase {
   virtual int stats(double* out, int reset, cudaStream_t s) = 0;
   virtual int debug(long long env, double* M, double* bias, double* qacc, double* fc, int32_t* info, double* con, double* cache) = 0;
   int64_t launches = 0;
+  virtual void tier_steps(int64_t* lite, int64_t* full) const { *lite = 0; *full = 0; }
+  virtual int64_t last_overflow() const { return 0; }
   int arena_bytes = 0, blocks_per_sm = 0, regs = 0, device = 0, state_bytes = 0, wpb = 0;
+  int lite_arena_bytes = 0, lite_blocks_per_sm = 0, lite_regs = 0, lite_wpb = 0;   // zero when the model has no lite size class
   long long n = 0;
 };
 

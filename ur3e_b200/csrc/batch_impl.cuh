@@ -2,7 +2,9 @@
 // One warp per environment, WPB warps per block, one shared-memory Arena per warp (engine.cuh / env.cuh).
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "batch_base.h"
@@ -16,12 +18,16 @@
 namespace ur3e {
 enum Op { OP_STEP = 0, OP_RESET = 1, OP_SET_STATE = 2, OP_DEBUG = 3 };
 
-template <typename Real, typename D>
+template <typename Real>
 struct KArgs {
   const DevModel<Real>* m;
   EnvCfg<Real> c;
   SolverOpts<Real> opt;
-  EnvState<Real, D>* st;
+  void* st;   // EnvState<Real, D>[n]; the lite and full size classes of a model share the record layout
+  // two-tier stepping (see Batch::step): overflow hand-off from the lite kernel to the full kernel
+  int* ovf_count; int* ovf_list;         // lite tier: environments whose rows / contacts exceeded the lite caps (not stored)
+  const int* list_count; const int* list;  // full tier: process exactly these environments
+  int lite_maxcon, lite_maxefc;          // full kernel used as the only tier: count the environments that would not fit lite
   long long n;
   int op;
   const Real* act; Real* obs; Real* rew; uint8_t* term; uint8_t* trunc; Real* final_obs;
@@ -43,39 +49,25 @@ template <typename Real, typename D> __host__ __device__ constexpr int warps_per
 constexpr int DBG_DOUBLES = MAXV * MAXV + 3 * MAXV + 8 + 4 * MAXCON + CACHE_SIZE;
 
 template <typename Real, typename D>
-__global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(const KArgs<Real, D> a) {
+__global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(const KArgs<Real> a) {
   constexpr int WPB = warps_per_block<Real, D>();
   extern __shared__ int4 smem_raw[];
   const int warp = threadIdx.x >> 5;
   long long e = (long long)blockIdx.x * WPB + warp;
   if (a.op == OP_DEBUG) { if (blockIdx.x != 0 || warp != 0) return; e = a.dbg_env; }
-  // OP_STEP uses block barriers: a warp past the end keeps running on the last environment and simply does not store
-  const bool live = e < a.n;
-  if (!live) { if (a.op != OP_STEP) return; e = a.n - 1; }
+  if (e >= a.n) return;
   Arena<Real, D>& s = *reinterpret_cast<Arena<Real, D>*>(reinterpret_cast<unsigned char*>(smem_raw) + warp * arena_stride<Real, D>());
   const DevModel<Real>& m = *a.m;
   const EnvCfg<Real>& c = a.c;
   constexpr int NW = sizeof(EnvState<Real, D>) / 16;
-  int4* gst = reinterpret_cast<int4*>(a.st + e);
+  int4* gst = reinterpret_cast<int4*>(static_cast<EnvState<Real, D>*>(a.st) + e);
   int4* sst = reinterpret_cast<int4*>(&s.st);
   if (a.op == OP_RESET && a.mask && !a.mask[e]) return;
   WARP_FOR(i, NW) sst[i] = gst[i];
   IF_LANE0 { s.overflow = 0; s.ncon = 0; s.nefc = 0; s.solver_iter = 0; }
   WARP_SYNC();
   const int od = c.obs_dim;
-  if (a.op == OP_STEP) {
-    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim);
-    const int done = r.terminated | r.truncated;
-    if (done && a.final_obs && live) { WARP_FOR(i, od) a.final_obs[e * od + i] = s.obs[i]; }
-    if (done && c.auto_reset) {
-      env_reset(m, c, s, a.opt, a.seed, a.env_base + (unsigned long long)e);
-      ContactFlags cf = contact_flags(m, c, s);
-      write_obs(m, c, s, cf);
-    }
-    if (!live) return;
-    WARP_FOR(i, od) a.obs[e * od + i] = s.obs[i];
-    IF_LANE0 { a.rew[e] = r.reward; a.term[e] = (uint8_t)r.terminated; a.trunc[e] = (uint8_t)r.truncated; }
-  } else if (a.op == OP_RESET) {
+  if (a.op == OP_RESET) {
     env_reset(m, c, s, a.opt, a.seed, a.env_base + (unsigned long long)e);
     ContactFlags cf = contact_flags(m, c, s);
     write_obs(m, c, s, cf);
@@ -108,6 +100,53 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
   WARP_FOR(i, NW) gst[i] = sst[i];
 }
 
+// The step path.  One warp per environment; the block's warps pass the substep phases together (block barriers), so every
+// warp of the block runs the same trip count: a warp without work repeats the last environment and does not store.
+template <typename Real, typename D>
+__global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) step_kernel(const KArgs<Real> a) {
+  constexpr int WPB = warps_per_block<Real, D>();
+  extern __shared__ int4 smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  Arena<Real, D>& s = *reinterpret_cast<Arena<Real, D>*>(reinterpret_cast<unsigned char*>(smem_raw) + warp * arena_stride<Real, D>());
+  const DevModel<Real>& m = *a.m;
+  const EnvCfg<Real>& c = a.c;
+  constexpr int NW = sizeof(EnvState<Real, D>) / 16;
+  const int od = c.obs_dim;
+  long long count = a.n; int iters = 1;
+  if (a.list) { count = *a.list_count; const long long per = (long long)gridDim.x * WPB; iters = (int)((count + per - 1) / per); }
+  for (int it = 0; it < iters; ++it) {
+    const long long idx = ((long long)it * gridDim.x + blockIdx.x) * WPB + warp;
+    const bool live = idx < count;
+    const long long e = a.list ? (long long)a.list[live ? idx : count - 1] : (live ? idx : count - 1);
+    int4* gst = reinterpret_cast<int4*>(static_cast<EnvState<Real, D>*>(a.st) + e);
+    int4* sst = reinterpret_cast<int4*>(&s.st);
+    WARP_FOR(i, NW) sst[i] = gst[i];
+    IF_LANE0 { s.overflow = 0; s.ncon = 0; s.nefc = 0; s.solver_iter = 0; }
+    WARP_SYNC();
+    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim);
+    if (a.ovf_list) {
+      // lite tier: this environment needed more rows / contacts than the lite arena holds; leave its stored state
+      // untouched and hand it to the full kernel
+      if (s.overflow) { IF_LANE0 { if (live) { int k = atomicAdd(a.ovf_count, 1); a.ovf_list[k] = (int)e; } } continue; }
+    } else if (a.lite_maxcon > 0 && live) {
+      if (s.max_ncon > a.lite_maxcon || s.max_nefc > a.lite_maxefc) { IF_LANE0 atomicAdd(a.ovf_count, 1); }
+    }
+    const int done = r.terminated | r.truncated;
+    if (done && a.final_obs && live) { WARP_FOR(i, od) a.final_obs[e * od + i] = s.obs[i]; }
+    if (done && c.auto_reset) {
+      env_reset(m, c, s, a.opt, a.seed, a.env_base + (unsigned long long)e);
+      ContactFlags cf = contact_flags(m, c, s);
+      write_obs(m, c, s, cf);
+    }
+    if (!live) continue;
+    WARP_FOR(i, od) a.obs[e * od + i] = s.obs[i];
+    IF_LANE0 { a.rew[e] = r.reward; a.term[e] = (uint8_t)r.terminated; a.trunc[e] = (uint8_t)r.truncated; }
+    WARP_SYNC();
+    WARP_FOR(i, NW) gst[i] = sst[i];
+    WARP_SYNC();
+  }
+}
+
 template <typename Real, typename D>
 __global__ void state_io_kernel(EnvState<Real, D>* st, long long n, int nq, int nv, Real* qpos, Real* qvel, Real* ws) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -130,25 +169,33 @@ __global__ void stats_kernel(EnvState<Real, D>* st, long long n, double* out, in
   }
 }
 
-template <typename Real, typename D>
+template <typename Real, typename D, typename DL = D>
 struct Batch : BatchBase {
+  static constexpr bool HAS_LITE = !std::is_same<D, DL>::value;
+  static_assert(sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DL>), "lite and full size classes must share the record layout");
+  int *d_ovf_count = nullptr, *d_ovf_list = nullptr, *h_ovf = nullptr; cudaEvent_t ovf_ev = nullptr; bool ovf_pending = false, heavy = false;
+  long long lite_steps = 0, full_steps = 0;
+  void tier_steps(int64_t* lite, int64_t* full) const override { *lite = lite_steps; *full = full_steps; }
+  int64_t last_overflow() const override { return h_ovf ? *h_ovf : 0; }
   DevModel<Real>* d_model = nullptr;
   EnvState<Real, D>* d_state = nullptr;
-  KArgs<Real, D> base;
+  KArgs<Real> base;
   HostModel hm;
   int act_dim = 0, obs_dim = 0;
   // staging for the host-buffer entry point
   Real *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr; uint8_t *d_term = nullptr, *d_trunc = nullptr; double* d_dbg = nullptr;
   cudaStream_t own_stream = nullptr;
   uint64_t seed = 0;
+  int sm_count = 148;
 
   ~Batch() override {
     cudaSetDevice(device);
+    cudaFree(d_ovf_count); cudaFree(d_ovf_list); if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev);
     cudaFree(d_model); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
   static constexpr int WPB = warps_per_block<Real, D>();
-  int launch(KArgs<Real, D>& a, cudaStream_t s, long long envs) {
+  int launch(KArgs<Real>& a, cudaStream_t s, long long envs) {
     size_t smem = arena_stride<Real, D>() * WPB;
     unsigned blocks = (unsigned)((envs + WPB - 1) / WPB);
     env_kernel<Real, D><<<blocks, WPB * 32, smem, s>>>(a);
@@ -212,21 +259,75 @@ struct Batch : BatchBase {
     cudaFuncAttributes fa; CUDA_OK(cudaFuncGetAttributes(&fa, env_kernel<Real, D>));
     wpb = WPB; regs = fa.numRegs; arena_bytes = (int)arena_stride<Real, D>(); state_bytes = (int)sizeof(EnvState<Real, D>);
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, env_kernel<Real, D>, WPB * 32, smem));
+    CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, dev)); sm_count = prop.multiProcessorCount;
+    if constexpr (HAS_LITE) {
+      constexpr int WL = warps_per_block<Real, DL>();
+      CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
+      CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int))); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
+      CUDA_OK(cudaMallocHost(&h_ovf, sizeof(int))); *h_ovf = 0;
+      CUDA_OK(cudaEventCreateWithFlags(&ovf_ev, cudaEventDisableTiming));
+      cudaFuncAttributes fl; CUDA_OK(cudaFuncGetAttributes(&fl, step_kernel<Real, DL>));
+      lite_wpb = WL; lite_arena_bytes = (int)arena_stride<Real, DL>(); lite_regs = fl.numRegs;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lite_blocks_per_sm, step_kernel<Real, DL>, WL * 32, arena_stride<Real, DL>() * WL));
+    }
+    { cudaFuncAttributes fs; CUDA_OK(cudaFuncGetAttributes(&fs, step_kernel<Real, D>)); regs = fs.numRegs;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, step_kernel<Real, D>, WPB * 32, smem)); }
     CUDA_OK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     return 0;
   }
   int reset(const uint8_t* mask, uint64_t sd, void* obs, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
     seed = sd;
-    KArgs<Real, D> a = base; a.op = OP_RESET; a.mask = mask; a.seed = sd; a.obs = (Real*)obs;
+    KArgs<Real> a = base; a.op = OP_RESET; a.mask = mask; a.seed = sd; a.obs = (Real*)obs;
     return launch(a, s, n);
+  }
+  template <typename DD> int launch_step(KArgs<Real>& a, cudaStream_t s, unsigned blocks) {
+    constexpr int W = warps_per_block<Real, DD>();
+    step_kernel<Real, DD><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    return 0;
   }
   int step(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc, void* fobs, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
     if (!act || !obs || !rew || !term || !trunc) return set_err("step: null buffer");
-    KArgs<Real, D> a = base; a.op = OP_STEP; a.seed = seed;
+    KArgs<Real> a = base; a.op = OP_STEP; a.seed = seed;
     a.act = (const Real*)act; a.obs = (Real*)obs; a.rew = (Real*)rew; a.term = term; a.trunc = trunc; a.final_obs = (Real*)fobs;
-    return launch(a, s, n);
+    constexpr int WF = warps_per_block<Real, D>();
+    const unsigned full_blocks = (unsigned)((n + WF - 1) / WF);
+    if constexpr (!HAS_LITE) return launch_step<D>(a, s, full_blocks);
+    else {
+      // Two tiers.  The lite size class (small row / contact caps -> small arena -> more resident warps) steps every
+      // environment; the few that exceed its caps are left untouched and re-stepped by the full size class from a device-side
+      // list.  When more than a quarter of the batch overflows (e.g. a whole batch in grasp) the full class runs alone.  The
+      // overflow count is read back asynchronously (one step late), so stepping never synchronises with the host.
+      if (ovf_pending && cudaEventQuery(ovf_ev) == cudaSuccess) {
+        ovf_pending = false;
+        const long long cnt = *h_ovf;
+        heavy = heavy ? cnt > n / 8 : cnt > n / 4;
+      }
+      CUDA_OK(cudaMemsetAsync(d_ovf_count, 0, sizeof(int), s));
+      if (heavy) {
+        a.ovf_count = d_ovf_count; a.lite_maxcon = DL::MAXCON; a.lite_maxefc = DL::MAXEFC;
+        if (int rc = launch_step<D>(a, s, full_blocks)) return rc;
+        ++full_steps;
+      } else {
+        constexpr int WL = warps_per_block<Real, DL>();
+        KArgs<Real> l = a; l.ovf_count = d_ovf_count; l.ovf_list = d_ovf_list;
+        if (int rc = launch_step<DL>(l, s, (unsigned)((n + WL - 1) / WL))) return rc;
+        a.list_count = d_ovf_count; a.list = d_ovf_list;
+        unsigned tail_blocks = (unsigned)(2 * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;
+        if (int rc = launch_step<D>(a, s, tail_blocks)) return rc;
+        ++lite_steps;
+      }
+      if (!ovf_pending) {
+        CUDA_OK(cudaMemcpyAsync(h_ovf, d_ovf_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CUDA_OK(cudaEventRecord(ovf_ev, s));
+        ovf_pending = true;
+      }
+      return 0;
+    }
   }
   int ensure_staging() {
     if (d_act) return 0;
@@ -258,7 +359,7 @@ struct Batch : BatchBase {
   int set_state(const void* qpos, const void* qvel, const void* ws, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
     if (!qpos || !qvel) return set_err("set_state: null buffer");
-    KArgs<Real, D> a = base; a.op = OP_SET_STATE; a.qpos_in = (const Real*)qpos; a.qvel_in = (const Real*)qvel; a.ws_in = (const Real*)ws;
+    KArgs<Real> a = base; a.op = OP_SET_STATE; a.qpos_in = (const Real*)qpos; a.qvel_in = (const Real*)qvel; a.ws_in = (const Real*)ws;
     return launch(a, s, n);
   }
   int stats(double* out, int rst, cudaStream_t s) override {
@@ -274,7 +375,7 @@ struct Batch : BatchBase {
     if (env < 0 || env >= n) return set_err("debug: env out of range");
     if (!d_dbg) CUDA_OK(cudaMalloc(&d_dbg, sizeof(double) * DBG_DOUBLES));
     CUDA_OK(cudaMemset(d_dbg, 0, sizeof(double) * DBG_DOUBLES));
-    KArgs<Real, D> a = base; a.op = OP_DEBUG; a.dbg_env = env; a.dbg = d_dbg;
+    KArgs<Real> a = base; a.op = OP_DEBUG; a.dbg_env = env; a.dbg = d_dbg;
     if (int rc = launch(a, 0, 1)) return rc;
     std::vector<double> hbuf(DBG_DOUBLES);
     CUDA_OK(cudaMemcpy(hbuf.data(), d_dbg, sizeof(double) * DBG_DOUBLES, cudaMemcpyDeviceToHost));
@@ -295,9 +396,9 @@ struct Batch : BatchBase {
 };
 
 
-template <typename Real, typename D>
+template <typename Real, typename D, typename DL = D>
 std::unique_ptr<BatchBase> make_batch(const HostModel& h, const ur3e_env_config& cfg, long long n, int device) {
-  auto p = std::make_unique<Batch<Real, D>>();
+  auto p = std::make_unique<Batch<Real, D, DL>>();
   if (p->init(h, cfg, n, device)) return nullptr;
   return p;
 }

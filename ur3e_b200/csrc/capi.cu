@@ -93,6 +93,12 @@ int ur3e_batch_kernel_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t* w
   if (arena_bytes) *arena_bytes = b->impl->arena_bytes; if (wpb) *wpb = b->impl->wpb; if (blocks_per_sm) *blocks_per_sm = b->impl->blocks_per_sm; if (regs) *regs = b->impl->regs;
   return 0;
 }
+int ur3e_batch_tier_info(const ur3e_batch* b, int64_t* o) {
+  GUARD(b); if (!o) return set_err("null argument");
+  int64_t l = 0, f = 0; b->impl->tier_steps(&l, &f);
+  o[0] = b->impl->lite_arena_bytes; o[1] = b->impl->lite_wpb; o[2] = b->impl->lite_blocks_per_sm; o[3] = b->impl->lite_regs; o[4] = l; o[5] = f; o[6] = b->impl->last_overflow(); o[7] = 0;
+  return 0;
+}
 int ur3e_batch_state_bytes(const ur3e_batch* b) { return (b && b->impl) ? b->impl->state_bytes : -1; }
 
 }  // extern "C"

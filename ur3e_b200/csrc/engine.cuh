@@ -23,6 +23,7 @@ struct Dims {
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // assets/ur3e_raw.xml
 using DimsGrip = Dims<23, 14, 14, 7, 6, 12, 16, 64>;    // assets/ur3e_2f85.xml
 using DimsMain = Dims<25, 20, 21, 7, 7, 16, 24, 96>;   // assets/main.xml
+using DimsMainLite = Dims<25, 20, 21, 7, 7, 16, 10, 48>;   // same model, caps for the common case (<= 10 contacts, <= 48 rows)
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 
@@ -66,7 +67,7 @@ struct Arena {
   int grp_mask[D::NGRP];
   uint8_t grp_row0[D::NGRP], grp_nrow[D::NGRP];
   uint8_t stage_n[D::NPAIR], stage_off[D::NPAIR];
-  int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad;
+  int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad, max_ncon, max_nefc;
   union {
     struct { Real cinert[D::NB][10], crb[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6], fbuf[D::NV][6]; } dyn;
     Real stage[D::NPAIR][STAGE_PTS][7];  // pos 3, normal 3, dist

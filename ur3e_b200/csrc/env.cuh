@@ -258,10 +258,13 @@ UR3E_PHASE StepOut<Real> env_step(const DevModel<Real>& m, const EnvCfg<Real>& c
   controller(m, c, s, act);
   int warn = 0;
   float sn = 0, sc = 0, si = 0;
+  int mxc = 0, mxe = 0;
   for (int k = 0; k < c.frame_skip; ++k) {
     warn |= substep(m, s, opt);
     sn += (float)s.nefc; sc += (float)s.ncon; si += (float)s.solver_iter;
+    mxc = s.ncon > mxc ? s.ncon : mxc; mxe = s.nefc > mxe ? s.nefc : mxe;
   }
+  IF_LANE0 { s.max_ncon = mxc; s.max_nefc = mxe; }
   update_cache(m, c, s);
   ContactFlags cf = contact_flags(m, c, s);
   write_obs(m, c, s, cf);
