@@ -33,7 +33,7 @@ static int run(const HostModel& h, const double* qpos, const double* qvel, const
   for (int k = 0; k < nsteps; ++k) w |= substep(m, *s, opt);
   for (int i = 0; i < h.nq; ++i) oq[i] = s->st.qpos[i];
   for (int i = 0; i < h.nv; ++i) { ov[i] = s->st.qvel[i]; oa[i] = nsteps == 0 ? s->qacc[i] : s->st.qacc_ws[i]; obias[i] = s->qfrc_bias[i]; ofc[i] = s->qfrc_constraint[i]; }
-  for (int i = 0; i < h.nv; ++i) for (int j = 0; j < h.nv; ++j) oM[i * h.nv + j] = s->M[i][j];
+  for (int i = 0; i < h.nv; ++i) for (int j = 0; j < h.nv; ++j) { int hi = i > j ? i : j, lo = i > j ? j : i; oM[i * h.nv + j] = s->M[hi * (hi + 1) / 2 + lo]; }
   info[0] = s->ncon; info[1] = s->nefc; info[2] = s->solver_iter; info[3] = w; info[4] = s->overflow; info[5] = (int)sizeof(Arena<Real, D>);
   return 0;
 }

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
     update_cache(m, c, s);
     double* o = a.dbg;
     const int nv = m.nv;
-    WARP_FOR(i, nv * nv) o[i] = (double)s.M[i / nv][i % nv];
+    WARP_FOR(i, nv * nv) { int r = i / nv, c2 = i % nv, hi = r > c2 ? r : c2, lo = r > c2 ? c2 : r; o[i] = (double)s.M[hi * (hi + 1) / 2 + lo]; }
     o += MAXV * MAXV;
     WARP_FOR(i, nv) { o[i] = (double)s.qfrc_bias[i]; o[MAXV + i] = (double)s.qacc[i]; o[2 * MAXV + i] = (double)s.qfrc_constraint[i]; }
     o += 3 * MAXV;

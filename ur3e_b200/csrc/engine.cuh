@@ -22,8 +22,8 @@ struct Dims {
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // assets/ur3e_raw.xml
 using DimsGrip = Dims<23, 14, 14, 7, 6, 12, 16, 64>;    // assets/ur3e_2f85.xml
-using DimsMain = Dims<25, 20, 21, 7, 7, 16, 24, 96>;   // assets/main.xml
-using DimsMainLite = Dims<25, 20, 21, 7, 7, 16, 10, 48>;   // same model, caps for the common case (<= 10 contacts, <= 48 rows)
+using DimsMain = Dims<25, 20, 21, 7, 7, 13, 24, 96>;   // assets/main.xml
+using DimsMainLite = Dims<25, 20, 21, 7, 7, 13, 8, 40>;   // same model, caps for the common case (<= 8 contacts, <= 40 rows)
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 
@@ -46,18 +46,18 @@ struct alignas(16) EnvState {
 template <typename Real, typename D>
 struct Arena {
   EnvState<Real, D> st;
-  Real qacc[D::NV], ctrl[D::NU], act_force[D::NU], obs[32];
+  Real qacc[D::NV], ctrl[D::NU], act_force[D::NU];
   Real xpos[D::NB][3];
   union {   // body frames are dead once the constraint rows exist; the Newton / Euler matrix reuses their storage
     struct { Real xquat[D::NB][4], xmat[D::NB][9], xipos[D::NB][3]; } k;
     struct { alignas(16) Real H[D::NV + 1][D::HS]; } n;   // rows padded to a multiple of 4
   } fr;
-  alignas(16) Real colbuf[2][32];
+  union { alignas(16) Real colbuf[2][32]; Real obs[32]; };   // solver scratch / the step's observation (written after the last solve)
   Real dinv[D::NV];
   Real cdof[D::NV][6];
-  Real M[D::NV][D::NV];
+  Real M[D::NV * (D::NV + 1) / 2];   // packed lower triangle, M(i,j) at i(i+1)/2 + j for j <= i
   Real qfrc_smooth[D::NV], qfrc_bias[D::NV], qfrc_constraint[D::NV], grad[D::NV], search[D::NV], Ma[D::NV], Mv[D::NV];
-  Real geom_xpos[D::NG][3], geom_xmat[D::NG][9], site_xpos[D::NS][3], site_xmat[D::NS][9], site_velp[D::NS][3];
+  Real geom_xpos[D::NG][3], geom_xmat[D::NG][9], site_xpos[D::NS][3], site_xmat[1][9] /* tcp only */, site_velp[D::NS][3];
   Real con_pos[D::MAXCON][3], con_dist[D::MAXCON], con_mu[D::MAXCON];
   union { Real frame[D::MAXCON][9]; Real H[D::MAXCON][6]; } cu;   // contact frames (row assembly) / cone Hessians (solver)
   Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_force[D::MAXEFC], efc_jar[D::MAXEFC], efc_jv[D::MAXEFC], efc_Dact[D::MAXEFC];
@@ -69,7 +69,7 @@ struct Arena {
   uint8_t stage_n[D::NPAIR], stage_off[D::NPAIR];
   int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad, max_ncon, max_nefc;
   union {
-    struct { Real cinert[D::NB][10], crb[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6], fbuf[D::NV][6]; } dyn;
+    struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
     Real stage[D::NPAIR][STAGE_PTS][7];  // pos 3, normal 3, dist
     Real efc_J[D::MAXEFC][D::NV];
   } u;
@@ -165,6 +165,15 @@ template <typename Real> UR3E_HD void cross_force(Real* r, const Real* vel, cons
   r[0] = a[0] + b[0]; r[1] = a[1] + b[1]; r[2] = a[2] + b[2]; r[3] = c[0]; r[4] = c[1]; r[5] = c[2];
 }
 
+// row i of (symmetric, packed lower-triangular) A times x
+template <typename Real> UR3E_HD Real sym_matvec_row(const Real* A, const Real* x, int i, int n) {
+  Real v = 0;
+  const Real* row = A + i * (i + 1) / 2;
+  for (int k = 0; k <= i; ++k) v += row[k] * x[k];
+  for (int k = i + 1; k < n; ++k) v += A[k * (k + 1) / 2 + i] * x[k];
+  return v;
+}
+
 // ---------------------------------------------------------------- kinematics
 template <typename Real, typename D>
 UR3E_HD void fk_body(const DevModel<Real>& m, Arena<Real, D>& s, int b) {
@@ -241,7 +250,7 @@ UR3E_PHASE void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
       int j = i - m.ngeom, b = m.site_body[j]; Real v[3], q[4];
       mat_vec3(v, s.fr.k.xmat[b], m.site_pos[j]);
       for (int k = 0; k < 3; ++k) s.site_xpos[j][k] = s.xpos[b][k] + v[k];
-      quat_mul(q, s.fr.k.xquat[b], m.site_quat[j]); quat2mat(s.site_xmat[j], q);
+      if (j == 0) { quat_mul(q, s.fr.k.xquat[b], m.site_quat[j]); quat2mat(s.site_xmat[0], q); }
     }
   }
   WARP_SYNC();
@@ -275,13 +284,8 @@ UR3E_PHASE void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
       for (int k = 0; k < 6; ++k) y.cvel[b][k] = cv[k];
     }
   }
-  WARP_FOR(i, nv * nv) (&s.M[0][0])[i] = 0;
+  WARP_FOR(i, nv * (nv + 1) / 2) s.M[i] = 0;
   WARP_SYNC();
-  // composite inertias: lane k carries component k down the (parent < child) body order
-  WARP_FOR(k, 10) {
-    for (int b = 0; b < nb; ++b) y.crb[b][k] = y.cinert[b][k];
-    for (int b = nb - 1; b > 0; --b) { int p = m.body_parent[b]; if (p > 0) y.crb[p][k] += y.crb[b][k]; }
-  }
   // cdof_dot = (velocity before the dof) x cdof   (mj_comVel)
   WARP_FOR(d, nv) {
     int b = m.dof_body[d], fk = m.dof_free_k[d];
@@ -295,9 +299,7 @@ UR3E_PHASE void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
     }
   }
   WARP_SYNC();
-  // M: f_i = crb(body_i) cdof_i ; M_ij = cdof_j . f_i
-  WARP_FOR(i, nv) mul_inert(y.fbuf[i], y.crb[m.dof_body[i]], s.cdof[i]);
-  // bias wrench of every body: I a + v x* I v, with a = -g + sum cdof_dot qvel over the chain
+  // bias wrench of every body: I a + v x* I v, with a = -g + sum cdof_dot qvel over the chain (needs the body's own inertia)
   WARP_FOR(b, nb) {
     Real* f = y.cfrc[b];
     if (b == 0 || m.body_lastdof[b] < 0) { for (int k = 0; k < 6; ++k) f[k] = 0; }
@@ -311,14 +313,22 @@ UR3E_PHASE void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
     }
   }
   WARP_SYNC();
+  // composite inertias in place (lanes 0-9: one inertia component each) and subtree bias wrenches (lanes 10-15), both serial
+  // down the (parent < child) body order
+  WARP_FOR(k, 16) {
+    if (k < 10) { for (int b = nb - 1; b > 0; --b) { int p = m.body_parent[b]; if (p > 0) y.cinert[p][k] += y.cinert[b][k]; } }
+    else { int c = k - 10; for (int b = nb - 1; b > 0; --b) { int p = m.body_parent[b]; if (p > 0) y.cfrc[p][c] += y.cfrc[b][c]; } }
+  }
+  WARP_SYNC();
+  // M: f_i = crb(body_i) cdof_i (stored over cdof_dot, which is dead) ; M_ij = cdof_j . f_i
+  WARP_FOR(i, nv) mul_inert(y.cdof_dot[i], y.cinert[m.dof_body[i]], s.cdof[i]);
+  WARP_SYNC();
   WARP_FOR(e, m.nM) {
     int i = m.M_i[e], j = m.M_j[e];
-    Real v = 0; for (int k = 0; k < 6; ++k) v += s.cdof[j][k] * y.fbuf[i][k];
+    Real v = 0; for (int k = 0; k < 6; ++k) v += s.cdof[j][k] * y.cdof_dot[i][k];
     if (i == j) v += m.dof_armature[i];
-    s.M[i][j] = v; s.M[j][i] = v;
+    s.M[i * (i + 1) / 2 + j] = v;
   }
-  WARP_FOR(k, 6) { for (int b = nb - 1; b > 0; --b) { int p = m.body_parent[b]; if (p > 0) y.cfrc[p][k] += y.cfrc[b][k]; } }
-  WARP_SYNC();
   // site linear velocities (mj_objectVelocity, world frame) for the observation
   WARP_FOR(j, m.nsite) {
     int b = m.site_body[j];
@@ -836,7 +846,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
   const int nv = m.nv, nefc = s.nefc;
   if (nefc == 0) {
     // unconstrained: qacc = M^-1 qfrc_smooth
-    WARP_FOR(i, nv * (nv + 1)) { int r = i / nv, c = i - r * nv; s.fr.n.H[r][c] = r < nv ? s.M[r][c] : s.qfrc_smooth[c]; }
+    WARP_FOR(i, nv * (nv + 1)) { int r = i / nv, c = i - r * nv; if (r < nv) { if (c <= r) s.fr.n.H[r][c] = s.M[r * (r + 1) / 2 + c]; } else s.fr.n.H[r][c] = s.qfrc_smooth[c]; }
     WARP_FOR(d, nv) s.qfrc_constraint[d] = 0;
     WARP_SYNC();
     chol_solve_aug(s, nv, s.qacc);
@@ -847,7 +857,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
   WARP_FOR(d, nv) s.qacc[d] = s.st.qacc_ws[d];
   WARP_SYNC();
   WARP_FOR(i, nv + nefc) {
-    if (i < nv) { Real v = 0; for (int k = 0; k < nv; ++k) v += s.M[i][k] * s.qacc[k]; s.Ma[i] = v; }
+    if (i < nv) s.Ma[i] = sym_matvec_row(s.M, s.qacc, i, nv);
     else { int r = i - nv; Real v = -s.efc_aref[r]; for (int k = 0; k < nv; ++k) v += s.u.efc_J[r][k] * s.qacc[k]; s.efc_jar[r] = v; }
   }
   WARP_SYNC();
@@ -872,7 +882,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
         int ab = m.tri_ab[e], a = ab >> 8, b = ab & 255;   // (a, b), b <= a, over the (nv+1) x (nv+1) lower triangle
         if (a == nv) { if (b < nv) s.fr.n.H[nv][b] = -s.grad[b]; }
         else {
-          Real h = s.M[a][b];
+          Real h = s.M[a * (a + 1) / 2 + b];
           if (a == b) {
             int k = m.dof_flrow[a];
             if (k >= 0) h += s.efc_Dact[ne + k];
@@ -911,7 +921,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
     chol_solve_aug(s, nv, s.search);
     // Mv, jv, and the quadratic (Gauss) part of the line cost
     WARP_FOR(i, nv + nefc) {
-      if (i < nv) { Real v = 0; for (int k = 0; k < nv; ++k) v += s.M[i][k] * s.search[k]; s.Mv[i] = v; }
+      if (i < nv) s.Mv[i] = sym_matvec_row(s.M, s.search, i, nv);
       else { int r = i - nv; Real v = 0; for (int k = 0; k < nv; ++k) v += s.u.efc_J[r][k] * s.search[k]; s.efc_jv[r] = v; }
     }
     WARP_SYNC();
@@ -984,7 +994,8 @@ UR3E_PHASE void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
     // (M + h diag(damping)) a = qfrc_smooth + qfrc_constraint   
     WARP_FOR(i, nv * (nv + 1)) {
       int r = i / nv, c = i - r * nv;
-      s.fr.n.H[r][c] = r < nv ? s.M[r][c] + (r == c ? h * m.dof_damping[r] : Real(0)) : s.qfrc_smooth[c] + s.qfrc_constraint[c];
+      if (r < nv) { if (c <= r) s.fr.n.H[r][c] = s.M[r * (r + 1) / 2 + c] + (r == c ? h * m.dof_damping[r] : Real(0)); }
+      else s.fr.n.H[r][c] = s.qfrc_smooth[c] + s.qfrc_constraint[c];
     }
     WARP_SYNC();
     chol_solve_aug(s, nv, s.search);

@@ -45,7 +45,7 @@ UR3E_PHASE void update_cache(const DevModel<Real>& m, const EnvCfg<Real>& c, Are
   WARP_FOR(i, CACHE_SIZE) {
     Real v;
     if (i < 3) v = s.site_xpos[site][i];
-    else if (i < 12) v = s.site_xmat[site][i - 3];
+    else if (i < 12) v = s.site_xmat[0][i - 3];   // the tcp is the first tracked site
     else if (i < 48) {
       int r = (i - 12) / 6, k = (i - 12) - 6 * r;
       if (r < 3) { Real col[3]; jac_col(m, s, k, s.site_xpos[site], b, col); v = col[r]; }
