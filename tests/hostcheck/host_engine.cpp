@@ -8,6 +8,7 @@
 
 #include "../../ur3e_b200/csrc/compile_model.h"
 #include "../../ur3e_b200/csrc/engine.cuh"
+#include "../../ur3e_b200/csrc/merge_bodies.h"
 
 using namespace ur3e;
 
@@ -21,7 +22,8 @@ static const HostModel& get_model(const char* path) {
 template <typename Real, typename D>
 static int run(const HostModel& h, const double* qpos, const double* qvel, const double* ctrl, const double* ws, int nsteps, int max_iter, double tol,
                double* oq, double* ov, double* oa, double* oM, double* obias, double* ofc, int* info) {
-  DevModel<Real> m = compile_model<Real>(h);
+  std::vector<int> bmap;
+  DevModel<Real> m = compile_model<Real>(merge_fixed_bodies(h, bmap));
   auto s = std::make_unique<Arena<Real, D>>();
   std::memset(s.get(), 0, sizeof(Arena<Real, D>));
   for (int i = 0; i < h.nq; ++i) s->st.qpos[i] = (Real)qpos[i];
@@ -43,8 +45,8 @@ extern "C" int hc_run(const char* xml, int use_float, const double* qpos, const 
   try {
     const HostModel& h = get_model(xml);
 #define GO(Real, D) return run<Real, D>(h, qpos, qvel, ctrl, ws, nsteps, max_iter, tol, oq, ov, oa, oM, obias, ofc, info)
-    if (h.nbody <= DimsRaw::NB && h.nv <= DimsRaw::NV && h.npair == 0) { if (use_float) GO(float, DimsRaw); else GO(double, DimsRaw); }
-    else if (h.nbody <= DimsGrip::NB && h.nv <= DimsGrip::NV) { if (use_float) GO(float, DimsGrip); else GO(double, DimsGrip); }
+    if (h.nv <= DimsRaw::NV && h.npair == 0) { if (use_float) GO(float, DimsRaw); else GO(double, DimsRaw); }
+    else if (h.nv <= DimsGrip::NV) { if (use_float) GO(float, DimsGrip); else GO(double, DimsGrip); }
     else { if (use_float) GO(float, DimsMain); else GO(double, DimsMain); }
   } catch (const std::exception& e) { std::fprintf(stderr, "hc_run: %s\n", e.what()); return -1; }
 }

@@ -9,6 +9,7 @@
 
 #include "batch_base.h"
 #include "compile_model.h"
+#include "merge_bodies.h"
 #include "env.cuh"
 
 #ifndef UR3E_BLOCKS_PER_SM
@@ -206,7 +207,11 @@ struct Batch : BatchBase {
   int init(const HostModel& h, const ur3e_env_config& cfg, long long n_envs, int dev) {
     device = dev; n = n_envs; hm = h;
     CUDA_OK(cudaSetDevice(dev));
-    DevModel<Real> m = compile_model<Real>(h);
+    std::vector<int> bmap;
+    const HostModel hmerged = merge_fixed_bodies(h, bmap);
+    if (hmerged.nbody > D::NB) return set_err("merged model has more bodies than the kernel size class");
+    DevModel<Real> m = compile_model<Real>(hmerged);
+    auto body = [&](const char* nm) { int b = h.name2id(OBJ_BODY, nm); return b >= 0 ? bmap[b] : -1; };
     CUDA_OK(cudaMalloc(&d_model, sizeof m)); CUDA_OK(cudaMemcpy(d_model, &m, sizeof m, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMalloc(&d_state, sizeof(EnvState<Real, D>) * n_envs)); CUDA_OK(cudaMemset(d_state, 0, sizeof(EnvState<Real, D>) * n_envs));
     std::memset(&base, 0, sizeof base);
@@ -218,19 +223,21 @@ struct Batch : BatchBase {
     for (int k = 0; k < 3; ++k) c.tool_rotvec[k] = (Real)cfg.tool_rotvec[k];
     auto tracked = [&](const char* nm) { for (int k = 0; k < m.nsite; ++k) if (std::string(tracked_site_names()[k]) == nm) return k; return -1; };
     c.site_tcp = tracked("tcp"); c.site_mug = tracked("handle_site"); c.site_pad = tracked("right_pad1_site");
-    c.body_mug = h.name2id(OBJ_BODY, "fish"); c.body_ghost = h.name2id(OBJ_BODY, "ghost");
-    c.body_lpad = h.name2id(OBJ_BODY, "left_pad"); c.body_rpad = h.name2id(OBJ_BODY, "right_pad"); c.body_table = h.name2id(OBJ_BODY, "table");
-    c.body_gripper_root = h.name2id(OBJ_BODY, "robotiq_base_mount"); c.body_gripper_last = -1;
-    if (c.body_gripper_root >= 0) {  // gym_utils.py:133-143: the subtree is a contiguous range in body order
+    c.body_mug = body("fish"); c.body_ghost = body("ghost");
+    c.body_lpad = body("left_pad"); c.body_rpad = body("right_pad"); c.body_table = body("table");
+    c.gripper_mask = 0;
+    {  // gym_utils.py:133-143: robotiq_base_mount and everything below it
       const auto& par = h.I("body_parentid");
-      int last = c.body_gripper_root;
-      for (int b = c.body_gripper_root + 1; b < h.nbody; ++b) { int a = b; while (a > c.body_gripper_root) a = par[a]; if (a == c.body_gripper_root) last = b; else break; }
-      c.body_gripper_last = last;
+      const int root = h.name2id(OBJ_BODY, "robotiq_base_mount");
+      if (root >= 0) {
+        const int outside = bmap[par[root]];   // a merged mount shares its new id with the arm link it is bolted to
+        for (int b = root; b < h.nbody; ++b) { int a = b; while (a > root) a = par[a]; if (a == root && bmap[b] != outside) c.gripper_mask |= 1u << bmap[b]; }
+      }
     }
     c.finger_q = 6;  // utils/utils.py:319-326 reads d.qpos[6] / d.qvel[6]
     c.topple_z = 0;
     if (c.body_mug >= 0) {
-      for (int g = 0; g < h.ngeom; ++g) if (h.I("geom_bodyid")[g] == c.body_mug) {  // utils/utils.py:193-196 get_body_size = first geom
+      for (int g = 0; g < h.ngeom; ++g) if (h.I("geom_bodyid")[g] == h.name2id(OBJ_BODY, "fish")) {  // utils/utils.py:193-196 get_body_size = first geom
         const double* sz = &h.D("geom_size")[3 * g];
         for (int k = 0; k < 3; ++k) c.mug_size[k] = (Real)sz[k];
         c.topple_z = (Real)(sz[0] > sz[1] ? sz[0] : sz[1]);

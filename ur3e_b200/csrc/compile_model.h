@@ -125,7 +125,7 @@ DevModel<Real> compile_model(const HostModel& h) {
     m.pair_friction[np][0] = (Real)h.D("pair_friction")[5 * p]; m.pair_friction[np][1] = (Real)h.D("pair_friction")[5 * p + 1];
     cp(m.pair_solref[np], h.D("pair_solref"), 2 * p, 2); cp(m.pair_solimp[np], h.D("pair_solimp"), 5 * p, 5);
     m.pair_margin[np] = (Real)h.D("pair_margin")[p]; m.pair_includemargin[np] = (Real)(h.D("pair_margin")[p] - h.D("pair_gap")[p]);
-    m.pair_invw[np] = (Real)(h.D("body_invweight0")[2 * gb[pg1[p]]] + h.D("body_invweight0")[2 * gb[pg2[p]]]);
+    m.pair_invw[np] = (Real)(h.D("geom_invweight0")[pg1[p]] + h.D("geom_invweight0")[pg2[p]]);
     ++np;
   }
   m.npair = np; m.ngeom = ng;
@@ -135,12 +135,12 @@ DevModel<Real> compile_model(const HostModel& h) {
     cp(m.eq_solref[e], h.D("eq_solref"), 2 * e, 2); cp(m.eq_solimp[e], h.D("eq_solimp"), 5 * e, 5);
     if (t == EQ_CONNECT) {
       m.eq_kind[e] = EK_CONNECT; m.eq_o1[e] = o1; m.eq_o2[e] = o2; cp(m.eq_data[e], h.D("eq_data"), 11 * e, 6);
-      m.eq_invw[e] = (Real)(h.D("body_invweight0")[2 * o1] + h.D("body_invweight0")[2 * o2]);
+      m.eq_invw[e] = (Real)h.D("eq_invweight0")[e];
     } else {
       req(t == EQ_JOINT, "equality type");
       req(jt[o1] == JNT_HINGE && (o2 < 0 || jt[o2] == JNT_HINGE), "joint equality needs hinge joints");
       m.eq_kind[e] = EK_JOINT; m.eq_o1[e] = jd[o1]; m.eq_o2[e] = o2 >= 0 ? jd[o2] : -1; cp(m.eq_data[e], h.D("eq_data"), 11 * e, 5);
-      m.eq_invw[e] = (Real)(h.D("dof_invweight0")[jd[o1]] + (o2 >= 0 ? h.D("dof_invweight0")[jd[o2]] : 0.0));
+      m.eq_invw[e] = (Real)h.D("eq_invweight0")[e];
     }
   }
   int ns = 0;

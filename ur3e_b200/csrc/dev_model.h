@@ -82,7 +82,8 @@ struct EnvCfg {
   int trunc_after_increment;  // v2 increments t before the truncation test (ur3e_env2.py:89-92); others test first
   int reset_key, reset_noise, auto_reset;
   int site_tcp, site_mug, site_pad, body_mug, body_ghost, body_lpad, body_rpad, finger_q;  // model indices (-1 when absent); sites index the tracked-site list
-  int body_table, body_gripper_root, body_gripper_last, pad_;  // gripper subtree = contiguous body range (gym_utils.py:133-143)
+  int body_table, pad0_, pad1_, pad_;
+  uint32_t gripper_mask;   // bit b: (merged) body b belongs to the robotiq_base_mount subtree (gym_utils.py:133-143)
   Real gains[24];          // CTRL_PID_TASK*: kp_pos[3] kd_pos[3] kp_rot[3] kd_rot[3]; CTRL_PD_JOINT: kp[6] kd[6]; CTRL_PINV: kp_p[6] kd_p[6] kp_r[6] kd_r[6]
   Real tool_rotvec[3];     // ur3e_env2.py:74
   Real act_low[8], act_high[8];

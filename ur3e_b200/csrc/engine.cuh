@@ -20,10 +20,10 @@ struct Dims {
   static constexpr int HS = ((NV_ + 1) | 1);   // odd row stride: one row per lane is conflict-free
   static constexpr int NGRP = MAXEQ + NPAIR;
 };
-using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // assets/ur3e_raw.xml
-using DimsGrip = Dims<23, 14, 14, 7, 6, 12, 16, 64>;    // assets/ur3e_2f85.xml
-using DimsMain = Dims<25, 20, 21, 7, 7, 13, 24, 96>;   // assets/main.xml
-using DimsMainLite = Dims<25, 20, 21, 7, 7, 13, 8, 40>;   // same model, caps for the common case (<= 8 contacts, <= 40 rows)
+using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // body counts are after fixed-body merging (merge_bodies.h)          // assets/ur3e_raw.xml
+using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 16, 64>;    // assets/ur3e_2f85.xml
+using DimsMain = Dims<19, 20, 21, 7, 7, 13, 24, 96>;   // assets/main.xml
+using DimsMainLite = Dims<19, 20, 21, 7, 7, 13, 8, 40>;   // same model, caps for the common case (<= 8 contacts, <= 40 rows)
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 
@@ -718,17 +718,22 @@ UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
 // runs column by column with the 1/diagonal saved during the factorisation.
 template <typename Real, typename D>
 UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
-  // factor (unscaled): after step k, raw[i][k] = L[i][k] * L[k][k]; exact zeros (block / tree sparsity of M + J^T D J) are skipped
+  // Factor (unscaled) with the forward substitution folded in: after step k, raw[i][k] = L[i][k] * L[k][k] and the
+  // right-hand side (kept in y) has had column k eliminated.  Exact zeros (block / tree sparsity of M + J^T D J) are skipped.
+  Real* y = s.colbuf[0];
+  WARP_FOR(k, n) y[k] = s.fr.n.H[n][k];
+  WARP_SYNC();
 #pragma unroll 1
-  for (int k = 0; k < n - 1; ++k) {
+  for (int k = 0; k < n; ++k) {
     Real d = s.fr.n.H[k][k];
     d = d > Num<Real>::minval ? d : Num<Real>::minval;
-    const Real inv = Real(1) / d;
+    const Real inv = Real(1) / d, yk = y[k];
     WARP_FOR(i, n) {
       if (i > k) {
         Real* row = s.fr.n.H[i];
         const Real t = row[k] * inv;
         if (t != 0) {
+          y[i] -= t * yk;
 #pragma unroll 4
           for (int j = k + 1; j <= i; ++j) row[j] -= t * s.fr.n.H[j][k];
         }
@@ -736,27 +741,25 @@ UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
     }
     WARP_SYNC();
   }
-  Real* y = s.colbuf[0];
+  // scale to the true factor once: L[i][k] = raw[i][k] / sqrt(d_k), z = L^-1 b, and keep 1 / L_kk
   WARP_FOR(k, n) {
     Real d = s.fr.n.H[k][k];
     d = d > Num<Real>::minval ? d : Num<Real>::minval;
-    s.dinv[k] = Real(1) / Num<Real>::sqrt(d);     // 1 / L_kk
-    y[k] = s.fr.n.H[n][k];                        // right-hand side
+    const Real rs = Real(1) / Num<Real>::sqrt(d);
+    s.dinv[k] = rs;
+    y[k] *= rs;
   }
   WARP_SYNC();
-  // forward substitution L y = b, L[i][k] = raw[i][k] * dinv[k]
-#pragma unroll 1
-  Real* z = s.colbuf[1];   // z = L^-1 b ; written once per entry, so one barrier per step suffices
-  for (int k = 0; k < n; ++k) {
-    const Real dk = s.dinv[k], yk = y[k] * dk;
-    WARP_FOR(i0, n - k) { int i = k + i0; if (i == k) z[i] = yk; else y[i] -= s.fr.n.H[i][k] * dk * yk; }
-    WARP_SYNC();
-  }
+  WARP_FOR(i, n) { Real* row = s.fr.n.H[i];
+#pragma unroll 4
+    for (int k = 0; k < i; ++k) row[k] *= s.dinv[k]; }
+  WARP_SYNC();
   // back substitution L^T x = z; x is only ever written
 #pragma unroll 1
   for (int k = n - 1; k >= 0; --k) {
-    const Real xk = z[k] * s.dinv[k];
-    WARP_FOR(i, k + 1) { if (i == k) x[i] = xk; else z[i] -= s.fr.n.H[k][i] * s.dinv[i] * xk; }
+    const Real xk = y[k] * s.dinv[k];
+    const Real* Lk = s.fr.n.H[k];
+    WARP_FOR(i, k + 1) { if (i == k) x[i] = xk; else y[i] -= Lk[i] * xk; }
     WARP_SYNC();
   }
 }

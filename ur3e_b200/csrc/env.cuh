@@ -113,7 +113,7 @@ UR3E_PHASE ContactFlags contact_flags(const DevModel<Real>& m, const EnvCfg<Real
       if (mug && (b1 == c.body_rpad || b2 == c.body_rpad)) f |= 2;
       bool tab = b1 == c.body_table || b2 == c.body_table;
       int other = b1 == c.body_table ? b2 : b1;
-      if (tab && c.body_gripper_root >= 0 && other >= c.body_gripper_root && other <= c.body_gripper_last) f |= 4;
+      if (tab && ((c.gripper_mask >> other) & 1u)) f |= 4;
     }
   }
   f = warp_or(f);

@@ -342,6 +342,15 @@ void set_const(HostModel& m) {
     tiw[t] = v;
   }
   set_array(m, "body_invweight0", biw, {nb, 2}); set_array(m, "dof_invweight0", diw, {nv}); set_array(m, "tendon_invweight0", tiw, {m.ntendon});
+  // per-geom / per-equality constraint weights, so that later model passes (fixed-body merging) cannot change them
+  V giw(m.ngeom, 0.0), eiw(m.neq, 0.0);
+  for (int g = 0; g < m.ngeom; ++g) giw[g] = biw[2 * m.I("geom_bodyid")[g]];
+  for (int e = 0; e < m.neq; ++e) {
+    int o1 = m.I("eq_obj1id")[e], o2 = m.I("eq_obj2id")[e];
+    if (m.I("eq_type")[e] == EQ_CONNECT) eiw[e] = biw[2 * o1] + biw[2 * o2];
+    else eiw[e] = diw[m.I("jnt_dofadr")[o1]] + (o2 >= 0 ? diw[m.I("jnt_dofadr")[o2]] : 0.0);
+  }
+  set_array(m, "geom_invweight0", giw, {m.ngeom}); set_array(m, "eq_invweight0", eiw, {m.neq});
 }
 
 }  // namespace
