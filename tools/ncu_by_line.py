@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Aggregate an ncu SASS source page by CUDA source line.
 
-usage: ncu_by_line.py <report.ncu-rep> <cubin> <kernel-substring> [top]
+usage: ncu_by_line.py <report.ncu-rep> <cubin> <ncu-kernel-name-substring> [top] [cubin-section-substring]
 Joins `ncu --page source --print-source sass --csv` (per-instruction counters) with `nvdisasm -g` line info
 of the same cubin (instruction order is identical), and prints the hottest source lines by executed
 warp-instructions and by stall samples.  Needs the build's -lineinfo.
@@ -10,6 +10,7 @@ import csv, re, subprocess, sys, collections, io
 
 rep, cubin, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+sect = sys.argv[5] if len(sys.argv) > 5 else "env_kernel"   # substring of the cubin .text section (mangled name)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 # split per kernel
@@ -30,7 +31,7 @@ lines = dis.split("\n")
 infn = False; cur_line = ("?", 0); seq = []
 for ln in lines:
     if ln.startswith("//--------------------- .text."):
-        infn = "env_kernel" in ln
+        infn = sect in ln
         continue
     if not infn:
         continue

@@ -844,28 +844,10 @@ UR3E_PHASE void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real
 
 template <typename Real> struct SolverOpts { int max_iter; int max_ls; Real tol; Real ls_tol; Real rtol; };
 
+// one Newton iteration; returns 0 = took a step, 1 = converged before stepping, 2 = took a (negligible) last step
 template <typename Real, typename D>
-UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
+UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, const Real scale) {
   const int nv = m.nv, nefc = s.nefc;
-  if (nefc == 0) {
-    // unconstrained: qacc = M^-1 qfrc_smooth
-    WARP_FOR(i, nv * (nv + 1)) { int r = i / nv, c = i - r * nv; if (r < nv) { if (c <= r) s.fr.n.H[r][c] = s.M[r * (r + 1) / 2 + c]; } else s.fr.n.H[r][c] = s.qfrc_smooth[c]; }
-    WARP_FOR(d, nv) s.qfrc_constraint[d] = 0;
-    WARP_SYNC();
-    chol_solve_aug(s, nv, s.qacc);
-    IF_LANE0 s.solver_iter = 0;
-    return;
-  }
-  const Real scale = Real(1) / (m.meaninertia * Real(nv > 1 ? nv : 1));
-  WARP_FOR(d, nv) s.qacc[d] = s.st.qacc_ws[d];
-  WARP_SYNC();
-  WARP_FOR(i, nv + nefc) {
-    if (i < nv) s.Ma[i] = sym_matvec_row(s.M, s.qacc, i, nv);
-    else { int r = i - nv; Real v = -s.efc_aref[r]; for (int k = 0; k < nv; ++k) v += s.u.efc_J[r][k] * s.qacc[k]; s.efc_jar[r] = v; }
-  }
-  WARP_SYNC();
-  int iter = 0;
-  for (; iter < opt.max_iter; ++iter) {
     constraint_update(m, s, true);
     Real gg = 0, gref = 0;
     WARP_FOR(d, nv) {
@@ -876,7 +858,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
     }
     gg = warp_sum(gg); gref = warp_sum(gref);
     // converged: MuJoCo's scaled-gradient test, or the gradient is at the rounding floor of its own terms
-    if (scale * Num<Real>::sqrt(gg) < opt.tol || gg < opt.rtol * opt.rtol * gref) break;
+    if (scale * Num<Real>::sqrt(gg) < opt.tol || gg < opt.rtol * opt.rtol * gref) return 1;
     // H = M + J^T diag(Dact) J + cone blocks ; augmented row = -grad.
     // phase A: M, the single-column rows (friction loss, limits) and the rhs row
     {
@@ -934,7 +916,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
     // exact line search: safeguarded Newton on phi'(alpha)
     Real p1, p2, lo = 0, hi = -1, alpha;
     line_eval(m, s, Real(0), g1, g2, &p1, &p2);
-    if (!(p1 < 0)) break;
+    if (!(p1 < 0)) return 1;
     const Real p10 = -p1;
     alpha = -p1 / p2;
     for (int ls = 0; ls < opt.max_ls; ++ls) {
@@ -952,7 +934,43 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
       else s.efc_jar[i - nv] += alpha * s.efc_jv[i - nv];
     }
     WARP_SYNC();
-    if (scale * alpha * Num<Real>::sqrt(sn) * m.meaninertia < opt.tol * Real(1e-3)) { ++iter; break; }
+    if (scale * alpha * Num<Real>::sqrt(sn) * m.meaninertia < opt.tol * Real(1e-3)) return 2;
+    return 0;
+}
+
+template <typename Real, typename D>
+UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, bool aligned = false) {
+  const int nv = m.nv, nefc = s.nefc;
+  if (nefc == 0) {
+    // unconstrained: qacc = M^-1 qfrc_smooth
+    WARP_FOR(i, nv * (nv + 1)) { int r = i / nv, c = i - r * nv; if (r < nv) { if (c <= r) s.fr.n.H[r][c] = s.M[r * (r + 1) / 2 + c]; } else s.fr.n.H[r][c] = s.qfrc_smooth[c]; }
+    WARP_FOR(d, nv) s.qfrc_constraint[d] = 0;
+    WARP_SYNC();
+    chol_solve_aug(s, nv, s.qacc);
+    IF_LANE0 s.solver_iter = 0;
+    // keep the block's barrier sequence: warps of the block that do have constraint rows iterate below
+    if (aligned) { for (int it = 0; it < opt.max_iter; ++it) if (!BLOCK_ANY(false)) break; }
+    return;
+  }
+  const Real scale = Real(1) / (m.meaninertia * Real(nv > 1 ? nv : 1));
+  WARP_FOR(d, nv) s.qacc[d] = s.st.qacc_ws[d];
+  WARP_SYNC();
+  WARP_FOR(i, nv + nefc) {
+    if (i < nv) s.Ma[i] = sym_matvec_row(s.M, s.qacc, i, nv);
+    else { int r = i - nv; Real v = -s.efc_aref[r]; for (int k = 0; k < nv; ++k) v += s.u.efc_J[r][k] * s.qacc[k]; s.efc_jar[r] = v; }
+  }
+  WARP_SYNC();
+  // Newton iterations.  In the aligned (regular substep) case the block's warps iterate in lock-step: a converged warp
+  // idles at the barrier while the others iterate, which keeps every warp of the block inside the same few KB of code.
+  int iter = 0;
+  bool done = false;
+  for (int it = 0; it < opt.max_iter; ++it) {
+    if (aligned) { if (!BLOCK_ANY(!done)) break; } else if (done) break;
+    if (!done) {
+      const int rc = newton_iteration(m, s, opt, scale);
+      if (rc != 1) ++iter;
+      done = rc != 0;
+    }
   }
   constraint_update(m, s, false);
   WARP_FOR(d, nv) { Real v = 0; for (int r = 0; r < nefc; ++r) v += s.u.efc_J[r][d] * s.efc_force[r]; s.qfrc_constraint[d] = v; }
@@ -975,7 +993,7 @@ UR3E_PHASE void forward(const DevModel<Real>& m, Arena<Real, D>& s, const Solver
     if (aligned) BLOCK_SYNC();
     make_constraint(m, s);
     if (aligned) BLOCK_SYNC();
-    solve(m, s, opt);
+    solve(m, s, opt, aligned);
   }
 }
 
