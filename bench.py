@@ -36,6 +36,7 @@ def parse():
     p.add_argument("--cpu-steps", type=int, default=0, help="env-steps per CPU worker for the cpu_baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-l2-flush", action="store_true", help="profiling aid: skip the L2 flush so that ncu's dram counters show the kernel's own traffic")
     return p.parse_args()
 
 
@@ -192,7 +193,8 @@ def main():
     launches0 = batch.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k in range(args.steps):
-        flush.zero_()                       # L2 flush between timed iterations (outside the per-step event pair)
+        if not args.no_l2_flush:
+            flush.zero_()                   # L2 flush between timed iterations (outside the per-step event pair)
         a = acts[k % NBUF] if acts is not None else mug_action(k)
         ev[k][0].record()
         batch.step(a, want_final_obs=False)
@@ -265,7 +267,14 @@ def main():
     sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     fp32_peak = props.multi_processor_count * 128 * 2 * sm_mhz * 1e6 / 1e12
     per_gpu_rate = n * args.steps / (total_ms * 1e-3)
-    roof = {"bound": "hbm", "achieved": bytes_per_env * n / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": None,
+    traffic = None
+    try:   # dram__bytes_read + dram__bytes_write of the dominant kernel from the committed ncu capture, scaled per launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if args.workload == "rollout" and args.dtype == "f32":
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * n / tj["envs"]
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "achieved": bytes_per_env * n / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s", "traffic": traffic,
             "peak_source": peak_src, "algorithmic_bytes_per_env_step": bytes_per_env,
             "note": "the path is FP32-pipe/latency bound, not HBM bound (SURVEY 8d): see roofline_fp32"}
     roof["frac"] = roof["achieved"] / roof["peak"]
