@@ -36,6 +36,7 @@ def parse():
     p.add_argument("--cpu-steps", type=int, default=0, help="env-steps per CPU worker for the cpu_baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--solver-iters", type=int, default=0, help="Newton iteration cap (0 = library default for the dtype)")
     p.add_argument("--no-l2-flush", action="store_true", help="profiling aid: skip the L2 flush so that ncu's dram counters show the kernel's own traffic")
     return p.parse_args()
 
@@ -143,7 +144,8 @@ def main():
     else:
         model = Model(asset("main.xml")); mname = "C"
         xml, kw, _, _ = presets.ENV_SPECS["gymnasium_env/ur3e-v2"]
-        cfg = presets.make_config(model, kw, auto_reset=1, env_id_base=rank * n, reset_noise=lib.NOISE_HIGH if args.workload == "rollout" else lib.NOISE_LOW)
+        cfg = presets.make_config(model, kw, auto_reset=1, env_id_base=rank * n, reset_noise=lib.NOISE_HIGH if args.workload == "rollout" else lib.NOISE_LOW,
+                                  solver_iterations=args.solver_iters)
     batch = SimBatch(model, cfg, n, local, dtype)
     obs0 = batch.reset(seed=0).clone()
     ki = batch.kernel_info()

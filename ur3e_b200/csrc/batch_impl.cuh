@@ -259,6 +259,7 @@ struct Batch : BatchBase {
     base.opt.tol = cfg.solver_tolerance > 0 ? (Real)cfg.solver_tolerance : (f64 ? Real(1e-15) : Real(1e-7));
     base.opt.max_ls = f64 ? 50 : 12; base.opt.ls_tol = f64 ? Real(1e-14) : Real(1e-5);
     base.opt.rtol = f64 ? Real(1e-15) : Real(2e-6);
+    base.opt.tol_improve = f64 ? Real(0) : Real(1e-8);   // MuJoCo's default solver tolerance (assets/*.xml do not override it)
     base.m = d_model; base.st = d_state; base.n = n_envs; base.env_base = (unsigned long long)cfg.env_id_base;
     act_dim = c.act_dim; obs_dim = c.obs_dim;
     size_t smem = arena_stride<Real, D>() * WPB;

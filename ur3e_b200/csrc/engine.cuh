@@ -842,7 +842,7 @@ UR3E_PHASE void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real
   *ddphi = g2 + warp_sum(p2);
 }
 
-template <typename Real> struct SolverOpts { int max_iter; int max_ls; Real tol; Real ls_tol; Real rtol; };
+template <typename Real> struct SolverOpts { int max_iter; int max_ls; Real tol; Real ls_tol; Real rtol; Real tol_improve; };
 
 // one Newton iteration; returns 0 = took a step, 1 = converged before stepping, 2 = took a (negligible) last step
 template <typename Real, typename D>
@@ -910,9 +910,9 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
       else { int r = i - nv; Real v = 0; for (int k = 0; k < nv; ++k) v += s.u.efc_J[r][k] * s.search[k]; s.efc_jv[r] = v; }
     }
     WARP_SYNC();
-    Real g1 = 0, g2 = 0, sn = 0;
-    WARP_FOR(d, nv) { g1 += s.search[d] * (s.Ma[d] - s.qfrc_smooth[d]); g2 += s.search[d] * s.Mv[d]; sn += s.search[d] * s.search[d]; }
-    g1 = warp_sum(g1); g2 = warp_sum(g2); sn = warp_sum(sn);
+    Real g1 = 0, g2 = 0, sn = 0, pred = 0;
+    WARP_FOR(d, nv) { g1 += s.search[d] * (s.Ma[d] - s.qfrc_smooth[d]); g2 += s.search[d] * s.Mv[d]; sn += s.search[d] * s.search[d]; pred -= s.search[d] * s.grad[d]; }
+    g1 = warp_sum(g1); g2 = warp_sum(g2); sn = warp_sum(sn); pred = Real(0.5) * warp_sum(pred);   // pred = Newton's model decrease of the cost
     // exact line search: safeguarded Newton on phi'(alpha)
     Real p1, p2, lo = 0, hi = -1, alpha;
     line_eval(m, s, Real(0), g1, g2, &p1, &p2);
@@ -935,6 +935,8 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
     }
     WARP_SYNC();
     if (scale * alpha * Num<Real>::sqrt(sn) * m.meaninertia < opt.tol * Real(1e-3)) return 2;
+    // MuJoCo's `improvement < tolerance` test (scaled cost decrease of this iteration); disabled (0) in the validation build
+    if (scale * pred < opt.tol_improve) return 2;
     return 0;
 }
 
