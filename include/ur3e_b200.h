@@ -28,7 +28,8 @@ enum { UR3E_OBJ_BODY = 1, UR3E_OBJ_JOINT = 3, UR3E_OBJ_GEOM = 5, UR3E_OBJ_SITE =
 enum { UR3E_CTRL_RAW = 0,          /* action = actuator ctrl (imitation_env_direct.py:90) */
        UR3E_CTRL_PD_JOINT = 1,     /* controller_func.py:128-167 pd_joint_ctrl + move_j.py:14-38 */
        UR3E_CTRL_PID_TASK = 2,     /* controller_func.py:68-117 pid_task_ctrl, action = 7-vector trajectory point (move_l_task.py:55-69) */
-       UR3E_CTRL_PID_TASK_ENV = 3  /* pid_task_ctrl behind the env action [x,y,z,grip] (ur3e_env2.py:72-82) */ };
+       UR3E_CTRL_PID_TASK_ENV = 3, /* pid_task_ctrl behind the env action [x,y,z,grip] (ur3e_env2.py:72-82) */
+       UR3E_CTRL_PINV = 4          /* controller/move_l.py:15-78: pinv(J) IK + two joint PDs, action = 7-vector trajectory point */ };
 enum { UR3E_OBS_STATE = 0, UR3E_OBS_V2 = 1, UR3E_OBS_V0 = 2, UR3E_OBS_DIRECT = 3 };
 enum { UR3E_REW_NONE = 0, UR3E_REW_V2 = 1, UR3E_REW_V0 = 2, UR3E_REW_MINUS1 = 3 };
 enum { UR3E_TERM_NONE = 0, UR3E_TERM_V2 = 1, UR3E_TERM_V0 = 2 };
@@ -48,9 +49,12 @@ typedef struct ur3e_env_config {
   int32_t auto_reset;     /* 1: finished envs are reset inside the step call (SB3 VecEnv semantics) */
   int32_t solver_iterations;   /* Newton iteration cap; 0 = default for dtype */
   double solver_tolerance;     /* scaled-gradient tolerance; 0 = default for dtype */
-  double gains[24];       /* PID_TASK*: kp_pos[3] kd_pos[3] kp_rot[3] kd_rot[3]; PD_JOINT: kp[6] kd[6] */
+  double gains[24];       /* PID_TASK*: kp_pos[3] kd_pos[3] kp_rot[3] kd_rot[3]; PD_JOINT: kp[6] kd[6]; PINV: kp_pos[6] kd_pos[6] kp_rot[6] kd_rot[6] */
   double tool_rotvec[3];  /* ur3e_env2.py:74 */
   int64_t env_id_base;    /* global index of env 0 of this batch (multi-GPU sharding: RNG streams are keyed by global id) */
+  int32_t single_tier;    /* 1: always step with the full size class (testing aid; default 0 = two-tier stepping where available) */
+  int32_t lite_max_contacts, lite_max_rows;   /* lower the lite tier's caps (0 = built-in 8 contacts / 40 rows); the full tier is unaffected */
+  int32_t reserved_;
 } ur3e_env_config;
 
 const char* ur3e_last_error(void);

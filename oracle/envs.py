@@ -168,8 +168,30 @@ class OracleCtrlLoop:
                 u = np.hstack([u, target[6] * self.m.py["actuator_ctrlrange"][-1][1]])
         elif self.mode == "pid_task":
             u = d.pid_task_ctrl(self.tcp, target, self.gains)
+        elif self.mode == "pinv":
+            u = self.pinv_ctrl(target)
         else:
             u = np.asarray(target, dtype=float)
         d.ctrl[:] = u
         d.step(1)
         return d.qpos.copy(), d.qvel.copy()
+
+
+def _pinv_ctrl(self, traj):
+    """controller/move_l.py:15-78 restated with numpy (np.linalg.pinv, as the reference)."""
+    d, m = self.d, self.m
+    jp, jr = d.jac_site(self.tcp)
+    tcp_pos = d.site_xpos.reshape(-1, 3)[self.tcp]; tcp_mat = d.site_xmat.reshape(-1, 9)[self.tcp]
+    errs = [traj[:3] - tcp_pos, O.rot_err(tcp_mat, traj[3:6])]
+    jr_rng = m.py["jnt_range"][:6]; cr = m.py["actuator_ctrlrange"][:6]
+    u = np.zeros(6); g = self.gains
+    for blk, (J, e) in enumerate(zip((jp[:, :6], jr[:, :6]), errs)):
+        dth = np.linalg.pinv(J) @ e
+        q = d.qpos[:6]
+        tq = np.clip(q + dth, jr_rng[:, 0], jr_rng[:, 1])
+        ub = g[12 * blk:12 * blk + 6] * (tq - q) + g[12 * blk + 6:12 * blk + 12] * -d.qvel[:6]
+        u += np.clip(ub, cr[:, 0], cr[:, 1])
+    return np.hstack([u, traj[6] * m.py["actuator_ctrlrange"][-1][1]])
+
+
+OracleCtrlLoop.pinv_ctrl = _pinv_ctrl

@@ -29,6 +29,7 @@ static int run(const HostModel& h, const double* qpos, const double* qvel, const
   for (int i = 0; i < h.nq; ++i) s->st.qpos[i] = (Real)qpos[i];
   for (int i = 0; i < h.nv; ++i) { s->st.qvel[i] = (Real)qvel[i]; s->st.qacc_ws[i] = (Real)ws[i]; }
   for (int i = 0; i < h.nu; ++i) s->ctrl[i] = (Real)ctrl[i];
+  s->cap_con = D::MAXCON; s->cap_efc = D::MAXEFC;
   SolverOpts<Real> opt{max_iter, 50, (Real)tol, (Real)(sizeof(Real) == 8 ? 1e-14 : 1e-5), (Real)(sizeof(Real) == 8 ? 1e-15 : 2e-6), (Real)(sizeof(Real) == 8 ? 0.0 : 1e-8)};
   int w = 0;
   if (nsteps == 0) forward(m, *s, opt, true);

@@ -50,7 +50,8 @@ def test_controllers_vs_reference_fixture():
     g = np.load(GOLD + "/controllers.npz")
     n = len(g["qpos"])
     m = Model(asset("ur3e_2f85.xml")); om = O.Model(asset("ur3e_2f85.xml")); od = O.Data(om)
-    for mode, gains, tgt, u_ref in ((lib.CTRL_PID_TASK, g["gains_task"], g["traj"], g["u_task"]), (lib.CTRL_PD_JOINT, g["gains_j"], g["target_j"], g["u_joint"])):
+    for mode, gains, tgt, u_ref in ((lib.CTRL_PID_TASK, g["gains_task"], g["traj"], g["u_task"]), (lib.CTRL_PD_JOINT, g["gains_j"], g["target_j"], g["u_joint"]),
+                                    (lib.CTRL_PINV, g["gains_pinv"], g["traj"], g["u_pinv"])):
         cfg = presets.make_config(m, dict(ctrl_mode=mode, obs_kind=lib.OBS_STATE, obs_dim=28, act_dim=7, frame_skip=1, gains=gains, reset_key="down"))
         b = SimBatch(m, cfg, n, 0, torch.float64)
         b.reset()
@@ -99,3 +100,36 @@ def test_controller_entry_points_track_targets():
     dbg = b.debug_forward(0)
     assert np.abs(dbg["tcp_pos"] - tl[0, :3]).max() < 0.02
     assert controller.task_space.pid_task_ctrl is controller.move_l.run
+
+
+def test_two_tier_stepping_f32():
+    """float32 main.xml batches step with the lite size class and hand environments that exceed its caps (built-in: 8 contacts
+    / 40 rows; lowered to 4 contacts here so that the fixture's grasp, 5-6 contacts, overflows) to the full class inside the
+    same step call.  The result must equal full-only
+    stepping, and the grasp episode of the v0 fixture must stay within the float32 drift bound of the reference trajectory."""
+    g = np.load(GOLD + "/env_v0.npz")
+    n = 64
+    mk = lambda **kw: UR3eVecEnv(IDS["v0"], n, dtype=torch.float32, auto_reset=False, reset_noise=lib.NOISE_NONE, **kw)
+    two, one = mk(lite_max_contacts=4), mk(single_tier=1)   # lite cap lowered to 4 contacts: any pad contact overflows
+    qp = torch.tensor(np.tile(g["qpos0"], (n, 1)), device="cuda", dtype=torch.float32); qv = torch.tensor(np.tile(g["qvel0"], (n, 1)), device="cuda", dtype=torch.float32)
+    for e in (two, one):
+        e.reset(); e.set_state(qp, qv)
+    handed_over, worst, worst_pair = 0, 0.0, 0.0
+    T = 220
+    for k in range(T):
+        a = torch.tensor(np.tile(g["actions"][k], (n, 1)), device="cuda", dtype=torch.float32)
+        # only an eighth of the batch grasps (below the quarter at which the full class takes over the whole batch): mixed
+        # populations exercise the device-side overflow list
+        a[n // 8:, 3] = 0.0
+        o2, r2, *_ = two.step(a); o1, r1, *_ = one.step(a)
+        torch.cuda.synchronize()
+        handed_over = max(handed_over, two.batch.kernel_info()["lite"]["last_overflow_envs"])
+        worst_pair = max(worst_pair, float((o2 - o1).abs().max()))
+        worst = max(worst, float(np.abs(o2[0, :9].double().cpu().numpy() - g["obs"][k][:9]).max()))
+    info = two.batch.kernel_info()["lite"]
+    assert info["lite_tier_steps"] == T and info["full_only_steps"] == 0
+    assert 0 < handed_over <= n // 8            # only the grasping environments ever overflow the lite caps
+    assert one.batch.kernel_info()["lite"]["full_only_steps"] == T
+    assert worst_pair < 1e-5, worst_pair         # two-tier == single-tier
+    assert worst < 5e-3, worst                   # float32 drift vs the float64 reference episode (tcp / mug / ghost positions)
+    assert int(o2[0, 9].item()) == int(g["obs"][T - 1][9])    # same grasp count as the reference at the end

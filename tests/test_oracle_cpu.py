@@ -57,6 +57,10 @@ def test_controllers_against_reference_fixture(assets):
         assert np.allclose(O.rot_err(d.site_xmat.reshape(-1, 9)[tcp], g["traj"][i][3:6]), g["rot_err"][i], atol=1e-10)
         assert rel(d.pd_joint_ctrl(g["target_j"][i][:6], g["gains_j"][:6], g["gains_j"][6:]), g["u_joint"][i][:6]) < 1e-12
         assert abs(g["u_joint"][i][6] - g["target_j"][i][6] * 255.0) < 1e-12                      # grip_ctrl
+    loop = OE.OracleCtrlLoop(assets + "/ur3e_2f85.xml", "pinv", g["gains_pinv"])                  # move_l.ctrl (pinv IK)
+    for i in range(len(g["qpos"])):
+        loop.set_state(g["qpos"][i], g["qvel"][i])
+        assert rel(loop.pinv_ctrl(g["traj"][i]), g["u_pinv"][i]) < 1e-9
 
 
 @pytest.mark.parametrize("kind", ["v2", "v0", "indirect"])

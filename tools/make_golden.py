@@ -67,7 +67,11 @@ def controller_vectors(seed):
         yj = yaml.safe_load(f)
     jg = {k: np.diag(v) for k, v in yj["qpos"].items()}     # move_j.py:50
     from controller.move_j import ctrl as move_j_ctrl      # move_j.py:14-27 (pd_joint_ctrl + grip_ctrl)
-    out = dict(qpos=[], qvel=[], traj=[], u_task=[], rot_err=[], target_j=[], u_joint=[])
+    from controller.move_l import ctrl as move_l_ctrl      # move_l.py:15-31 (pinv IK + two pd_joint_ctrl)
+    with open("controller/config/config_l.yml") as f:
+        yl = yaml.safe_load(f)
+    lp = {k: np.diag(v) for k, v in yl["pos"].items()}; lr = {k: np.diag(v) for k, v in yl["rot"].items()}
+    out = dict(qpos=[], qvel=[], traj=[], u_task=[], rot_err=[], target_j=[], u_joint=[], u_pinv=[])
     for _ in range(24):
         uu.reset(m, d, "down")
         d.qpos[:6] += rng.uniform(-0.5, 0.5, 6); d.qvel[:] = rng.uniform(-1, 1, m.nv)
@@ -78,9 +82,11 @@ def controller_vectors(seed):
         e = cf.get_rot_err(0, m, d, traj[3:6], np.zeros((1, 3)))
         tj = np.hstack([d.qpos[:6] + rng.uniform(-0.2, 0.2, 6), 0.3])
         uj = move_j_ctrl(0, m, d, tj, jg, np.zeros((1, 6)))
+        out["u_pinv"].append(move_l_ctrl(0, m, d, traj, lp, lr, np.zeros((1, 3)), np.zeros((1, 3))))
         out["qpos"].append(d.qpos.copy()); out["qvel"].append(d.qvel.copy()); out["traj"].append(traj); out["u_task"].append(u)
         out["rot_err"].append(e); out["target_j"].append(tj); out["u_joint"].append(uj)
     g = dict(gains_task=np.hstack([np.diag(pos_g["kp"]), np.diag(pos_g["kd"]), np.diag(rot_g["kp"]), np.diag(rot_g["kd"])]))
+    g["gains_pinv"] = np.hstack([np.diag(lp["kp"]), np.diag(lp["kd"]), np.diag(lr["kp"]), np.diag(lr["kd"])])
     if jg:
         g["gains_j"] = np.hstack([np.diag(jg["kp"]), np.diag(jg["kd"])])
     return {**{k: np.asarray(v) for k, v in out.items()}, **g}

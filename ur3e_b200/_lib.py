@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libur3e_b200.so")
 
 F32, F64 = 0, 1
 OBJ_BODY, OBJ_JOINT, OBJ_GEOM, OBJ_SITE, OBJ_TENDON, OBJ_ACTUATOR, OBJ_KEY = 1, 3, 5, 6, 18, 19, 23
-CTRL_RAW, CTRL_PD_JOINT, CTRL_PID_TASK, CTRL_PID_TASK_ENV = 0, 1, 2, 3
+CTRL_RAW, CTRL_PD_JOINT, CTRL_PID_TASK, CTRL_PID_TASK_ENV, CTRL_PINV = 0, 1, 2, 3, 4
 OBS_STATE, OBS_V2, OBS_V0, OBS_DIRECT = 0, 1, 2, 3
 REW_NONE, REW_V2, REW_V0, REW_MINUS1 = 0, 1, 2, 3
 TERM_NONE, TERM_V2, TERM_V0 = 0, 1, 2
@@ -26,7 +26,8 @@ class ModelDims(C.Structure):
 class EnvConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("ctrl_mode", "obs_kind", "reward_kind", "term_kind", "frame_skip", "act_dim", "obs_dim", "max_steps",
                                           "reset_key", "reset_noise", "auto_reset", "solver_iterations")] + [
-        ("solver_tolerance", C.c_double), ("gains", C.c_double * 24), ("tool_rotvec", C.c_double * 3), ("env_id_base", C.c_int64)]
+        ("solver_tolerance", C.c_double), ("gains", C.c_double * 24), ("tool_rotvec", C.c_double * 3), ("env_id_base", C.c_int64),
+        ("single_tier", C.c_int32), ("lite_max_contacts", C.c_int32), ("lite_max_rows", C.c_int32), ("reserved_", C.c_int32)]
 
 
 EXPORTS = ["ur3e_last_error", "ur3e_model_load", "ur3e_model_destroy", "ur3e_model_info", "ur3e_model_name2id", "ur3e_model_id2name",

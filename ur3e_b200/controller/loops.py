@@ -12,7 +12,7 @@ def run_trajectory(xml, ctrl_mode, gains, traj, n_envs=1, keyframe="down", devic
     """traj: [T, A] (shared by all envs) or [T, N, A] tensor/array of per-step targets.
     Returns (qpos [R, N, nq], qvel [R, N, nv]) recorded every `record_every` steps, and the SimBatch (for further stepping)."""
     model = Model(xml if "/" in xml else asset(xml))
-    act_dim = {_lib.CTRL_PD_JOINT: 7 if model.nu > 6 else 6, _lib.CTRL_PID_TASK: 7, _lib.CTRL_RAW: model.nu}[ctrl_mode]
+    act_dim = {_lib.CTRL_PD_JOINT: 7 if model.nu > 6 else 6, _lib.CTRL_PID_TASK: 7, _lib.CTRL_PINV: 7, _lib.CTRL_RAW: model.nu}[ctrl_mode]
     if batch is None:
         key = model.key_id(keyframe) if (keyframe is not None and model.nkey) else -1
         cfg = presets.make_config(model, dict(ctrl_mode=ctrl_mode, obs_kind=_lib.OBS_STATE, obs_dim=model.nq + model.nv, act_dim=act_dim,

@@ -29,6 +29,7 @@ struct KArgs {
   int* ovf_count; int* ovf_list;         // lite tier: environments whose rows / contacts exceeded the lite caps (not stored)
   const int* list_count; const int* list;  // full tier: process exactly these environments
   int lite_maxcon, lite_maxefc;          // full kernel used as the only tier: count the environments that would not fit lite
+  int cap_con, cap_efc;                  // row / contact caps of this launch (0 = the size class's own)
   long long n;
   int op;
   const Real* act; Real* obs; Real* rew; uint8_t* term; uint8_t* trunc; Real* final_obs;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
   int4* sst = reinterpret_cast<int4*>(&s.st);
   if (a.op == OP_RESET && a.mask && !a.mask[e]) return;
   WARP_FOR(i, NW) sst[i] = gst[i];
-  IF_LANE0 { s.overflow = 0; s.ncon = 0; s.nefc = 0; s.solver_iter = 0; }
+  IF_LANE0 { s.overflow = 0; s.ncon = 0; s.nefc = 0; s.solver_iter = 0; s.cap_con = D::MAXCON; s.cap_efc = D::MAXEFC; }
   WARP_SYNC();
   const int od = c.obs_dim;
   if (a.op == OP_RESET) {
@@ -122,7 +123,10 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) step_kernel(c
     int4* gst = reinterpret_cast<int4*>(static_cast<EnvState<Real, D>*>(a.st) + e);
     int4* sst = reinterpret_cast<int4*>(&s.st);
     WARP_FOR(i, NW) sst[i] = gst[i];
-    IF_LANE0 { s.overflow = 0; s.ncon = 0; s.nefc = 0; s.solver_iter = 0; }
+    IF_LANE0 {
+      s.overflow = 0; s.ncon = 0; s.nefc = 0; s.solver_iter = 0;
+      s.cap_con = (a.cap_con > 0 && a.cap_con < D::MAXCON) ? a.cap_con : D::MAXCON; s.cap_efc = (a.cap_efc > 0 && a.cap_efc < D::MAXEFC) ? a.cap_efc : D::MAXEFC;
+    }
     WARP_SYNC();
     StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim);
     if (a.ovf_list) {
@@ -175,7 +179,7 @@ struct Batch : BatchBase {
   static constexpr bool HAS_LITE = !std::is_same<D, DL>::value;
   static_assert(sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DL>), "lite and full size classes must share the record layout");
   int *d_ovf_count = nullptr, *d_ovf_list = nullptr, *h_ovf = nullptr; cudaEvent_t ovf_ev = nullptr; bool ovf_pending = false, heavy = false;
-  long long lite_steps = 0, full_steps = 0;
+  long long lite_steps = 0, full_steps = 0; bool single_tier = false; int lite_cap_con = DL::MAXCON, lite_cap_efc = DL::MAXEFC;
   void tier_steps(int64_t* lite, int64_t* full) const override { *lite = lite_steps; *full = full_steps; }
   int64_t last_overflow() const override { return h_ovf ? *h_ovf : 0; }
   DevModel<Real>* d_model = nullptr;
@@ -244,13 +248,13 @@ struct Batch : BatchBase {
         break;
       }
     }
-    bool needs_task = c.ctrl_mode == CTRL_PID_TASK || c.ctrl_mode == CTRL_PID_TASK_ENV;
+    bool needs_task = c.ctrl_mode == CTRL_PID_TASK || c.ctrl_mode == CTRL_PID_TASK_ENV || c.ctrl_mode == CTRL_PINV;
     if (needs_task && c.site_tcp < 0) return set_err("controller needs a 'tcp' site");
     if (c.obs_kind != OBS_STATE && (c.site_tcp < 0 || c.site_mug < 0 || c.body_ghost < 0 || c.body_mug < 0)) return set_err("observation kind needs the tcp/handle_site sites and the fish/ghost bodies (main.xml)");
     if (c.obs_kind == OBS_V0 && c.site_pad < 0) return set_err("OBS_V0 needs right_pad1_site");
     int want_obs = c.obs_kind == OBS_STATE ? h.nq + h.nv : c.obs_kind == OBS_V2 ? 24 : 13;
     if (c.obs_dim != want_obs || c.obs_dim > 32) return set_err("obs_dim does not match obs_kind (expected " + std::to_string(want_obs) + ")");
-    int want_act = c.ctrl_mode == CTRL_RAW ? h.nu : c.ctrl_mode == CTRL_PD_JOINT ? (h.nu > 6 ? 7 : 6) : c.ctrl_mode == CTRL_PID_TASK ? 7 : 4;
+    int want_act = c.ctrl_mode == CTRL_RAW ? h.nu : c.ctrl_mode == CTRL_PD_JOINT ? (h.nu > 6 ? 7 : 6) : (c.ctrl_mode == CTRL_PID_TASK || c.ctrl_mode == CTRL_PINV) ? 7 : 4;
     if (c.act_dim != want_act) return set_err("act_dim does not match ctrl_mode (expected " + std::to_string(want_act) + ")");
     if (c.frame_skip < 1) return set_err("frame_skip must be >= 1");
     if (c.reset_key >= h.nkey) return set_err("reset_key out of range");
@@ -261,7 +265,9 @@ struct Batch : BatchBase {
     base.opt.rtol = f64 ? Real(1e-15) : Real(2e-6);
     base.opt.tol_improve = f64 ? Real(0) : Real(1e-8);   // MuJoCo's default solver tolerance (assets/*.xml do not override it)
     base.m = d_model; base.st = d_state; base.n = n_envs; base.env_base = (unsigned long long)cfg.env_id_base;
-    act_dim = c.act_dim; obs_dim = c.obs_dim;
+    act_dim = c.act_dim; obs_dim = c.obs_dim; single_tier = cfg.single_tier != 0;
+    if (cfg.lite_max_contacts > 0 && cfg.lite_max_contacts < DL::MAXCON) lite_cap_con = cfg.lite_max_contacts;
+    if (cfg.lite_max_rows > 0 && cfg.lite_max_rows < DL::MAXEFC) lite_cap_efc = cfg.lite_max_rows;
     size_t smem = arena_stride<Real, D>() * WPB;
     CUDA_OK(cudaFuncSetAttribute(env_kernel<Real, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa; CUDA_OK(cudaFuncGetAttributes(&fa, env_kernel<Real, D>));
@@ -315,14 +321,15 @@ struct Batch : BatchBase {
         const long long cnt = *h_ovf;
         heavy = heavy ? cnt > n / 8 : cnt > n / 4;
       }
+      if (single_tier) heavy = true;
       CUDA_OK(cudaMemsetAsync(d_ovf_count, 0, sizeof(int), s));
       if (heavy) {
-        a.ovf_count = d_ovf_count; a.lite_maxcon = DL::MAXCON; a.lite_maxefc = DL::MAXEFC;
+        a.ovf_count = d_ovf_count; a.lite_maxcon = lite_cap_con; a.lite_maxefc = lite_cap_efc;
         if (int rc = launch_step<D>(a, s, full_blocks)) return rc;
         ++full_steps;
       } else {
         constexpr int WL = warps_per_block<Real, DL>();
-        KArgs<Real> l = a; l.ovf_count = d_ovf_count; l.ovf_list = d_ovf_list;
+        KArgs<Real> l = a; l.ovf_count = d_ovf_count; l.ovf_list = d_ovf_list; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc;
         if (int rc = launch_step<DL>(l, s, (unsigned)((n + WL - 1) / WL))) return rc;
         a.list_count = d_ovf_count; a.list = d_ovf_list;
         unsigned tail_blocks = (unsigned)(2 * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;

@@ -67,7 +67,7 @@ struct Arena {
   int grp_mask[D::NGRP];
   uint8_t grp_row0[D::NGRP], grp_nrow[D::NGRP];
   uint8_t stage_n[D::NPAIR], stage_off[D::NPAIR];
-  int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad, max_ncon, max_nefc;
+  int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
   union {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
     Real stage[D::NPAIR][STAGE_PTS][7];  // pos 3, normal 3, dist
@@ -510,13 +510,14 @@ UR3E_PHASE void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
     WARP_SYNC();
     int total = 0;
     for (int p = 0; p < m.npair; ++p) { int n = s.stage_n[p]; IF_LANE0 s.stage_off[p] = (uint8_t)total; total += n; }
-    int ncon = total > D::MAXCON ? D::MAXCON : total;
-    IF_LANE0 { s.ncon = ncon; if (total > D::MAXCON) s.overflow |= 1; }
+    const int capc = s.cap_con;   // <= D::MAXCON; smaller only when the caller lowers the cap (ur3e_env_config.lite_max_contacts)
+    int ncon = total > capc ? capc : total;
+    IF_LANE0 { s.ncon = ncon; if (total > capc) s.overflow |= 1; }
     WARP_SYNC();
     WARP_FOR(i, m.npair * STAGE_PTS) {
       int p = i / STAGE_PTS, c = i % STAGE_PTS;
       int o = s.stage_off[p] + c;
-      if (c < s.stage_n[p] && o < D::MAXCON) {
+      if (c < s.stage_n[p] && o < capc) {
         const Real* src = s.u.stage[p][c];
         for (int k = 0; k < 3; ++k) { s.con_pos[o][k] = src[k]; s.cu.frame[o][k] = src[3 + k]; }
         s.con_dist[o] = src[6]; s.con_pair[o] = (uint8_t)p;
@@ -580,8 +581,9 @@ UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nl = popcount32(mlo) + popcount32(mhi);
   int base_c = ne + nf + nl;
   int ncon = s.ncon;
-  if (base_c + 3 * ncon > D::MAXEFC) { ncon = (D::MAXEFC - base_c) / 3; if (ncon < 0) ncon = 0; IF_LANE0 { s.overflow |= 2; s.ncon = ncon; } }
-  int nefc = base_c + 3 * ncon; if (nefc > D::MAXEFC) nefc = D::MAXEFC;
+  const int cape = s.cap_efc;   // <= D::MAXEFC
+  if (base_c + 3 * ncon > cape) { ncon = (cape - base_c) / 3; if (ncon < 0) ncon = 0; IF_LANE0 { s.overflow |= 2; s.ncon = ncon; } }
+  int nefc = base_c + 3 * ncon; if (nefc > cape) nefc = cape;
   // row groups: rows that share one column set (used by the Hessian assembly)
   int ngrp = 0;
   {

@@ -93,6 +93,41 @@ UR3E_PHASE void controller(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena
       Real traj[7] = {act[0], act[1], act[2], c.tool_rotvec[0], c.tool_rotvec[1], c.tool_rotvec[2], act[3]};
       pid_task(m, c, s, traj); break;
     }
+    case CTRL_PINV: {
+      // move_l.py:15-78: dtheta = pinv(Jp[:, :6]) e_p and pinv(Jr[:, :6]) e_r (pinv = J^T (J J^T)^-1 for the full-row-rank 3 x 6
+      // blocks; numpy's SVD cut-off only differs at exact singularities), each through pd_joint_ctrl, summed; grip appended
+      const Real* ch = s.st.cache;
+      Real e[6], y[6];
+      for (int k = 0; k < 3; ++k) e[k] = act[k] - ch[k];
+      { Real rv[3] = {act[3], act[4], act[5]}; rot_err(ch + 3, rv, e + 3); }
+      for (int blk = 0; blk < 2; ++blk) {
+        const Real* J = ch + 12 + 18 * blk;   // 3 rows x 6 arm dofs
+        Real A[6];                            // J J^T, symmetric: 00 01 02 11 12 22
+        int idx = 0;
+        for (int r = 0; r < 3; ++r) for (int c2 = r; c2 < 3; ++c2) { Real v = 0; for (int k = 0; k < 6; ++k) v += J[6 * r + k] * J[6 * c2 + k]; A[idx++] = v; }
+        const Real c00 = A[3] * A[5] - A[4] * A[4], c01 = A[2] * A[4] - A[1] * A[5], c02 = A[1] * A[4] - A[2] * A[3];
+        const Real det = A[0] * c00 + A[1] * c01 + A[2] * c02, id = Real(1) / det;
+        const Real c11 = A[0] * A[5] - A[2] * A[2], c12 = A[1] * A[2] - A[0] * A[4], c22 = A[0] * A[3] - A[1] * A[1];
+        const Real* b = e + 3 * blk;
+        y[3 * blk + 0] = (c00 * b[0] + c01 * b[1] + c02 * b[2]) * id;
+        y[3 * blk + 1] = (c01 * b[0] + c11 * b[1] + c12 * b[2]) * id;
+        y[3 * blk + 2] = (c02 * b[0] + c12 * b[1] + c22 * b[2]) * id;
+      }
+      WARP_FOR(i, 6) {
+        const Real q = s.st.qpos[i], qd = s.st.qvel[i];
+        Real u = 0;
+        for (int blk = 0; blk < 2; ++blk) {
+          const Real* J = ch + 12 + 18 * blk;
+          const Real dth = J[i] * y[3 * blk] + J[6 + i] * y[3 * blk + 1] + J[12 + i] * y[3 * blk + 2];
+          Real tq = rmin(rmax(q + dth, m.dof_range[i][0]), m.dof_range[i][1]);
+          Real ub = c.gains[12 * blk + i] * (tq - q) + c.gains[12 * blk + 6 + i] * -qd;
+          u += rmin(rmax(ub, m.act_ctrlrange[i][0]), m.act_ctrlrange[i][1]);
+        }
+        s.ctrl[i] = u;
+      }
+      if (m.nu > 6) { IF_LANE0 s.ctrl[m.nu - 1] = act[6] * m.act_ctrlrange[m.nu - 1][1]; }
+      break;
+    }
     default: break;
   }
   WARP_SYNC();

@@ -12,6 +12,7 @@ GAINS_L_MUG = [220, 220, 120, 20, 20, 40, 35, 15, 15, 2, 2, 2]          # contro
 GAINS_V0 = [320, 320, 320, 20, 20, 25, 325, 325, 325, 2, 2, 2]          # ur3e_env.py:106-117
 GAINS_L_TASK = [120, 120, 120, 20, 20, 20, 35, 15, 15, 2, 2, 2]         # controller/config/config_l_task.yml
 GAINS_J = [20, 380, 300, 20, 30, 10, 5, 5, 5, 5, 5, 5]                  # controller/config/config_j.yml (kp[6] kd[6])
+GAINS_L_PINV = [20, 60, 20, 20, 20, 10, 5, 15, 5, 5, 5, 20, 5.02, 5.01, 5.80, 5.80, 5.09, 5.80, 5, 50, 10, 5, 5, 5]   # controller/config/config_l.yml (kp_pos kd_pos kp_rot kd_rot, per joint)
 MUG_DOWN_XY = (0.29799994, 0.13349916)                                  # assets/main.xml keyframe 'down'
 
 ENV_SPECS = {
