@@ -79,6 +79,12 @@ DevModel<Real> compile_model(const HostModel& h) {
     if (h.D("dof_damping")[d] > 0) damp = 1;
   }
   m.nfl = nfl; m.has_damping = damp;
+  m.max_nanc = 0;
+  for (int d = 0; d < h.nv; ++d) {
+    int na = 0;
+    for (int a = dpar[d]; a >= 0; a = dpar[a]) { req(na < MAXANC, "dof tree too deep"); m.dof_anc[d][na++] = a; }
+    m.dof_nanc[d] = na; if (na > m.max_nanc) m.max_nanc = na;
+  }
   int nM = 0;
   for (int i = 0; i < h.nv; ++i) for (int j = i; j >= 0; j = dpar[j]) { req(nM < MAXNM, "mass-matrix pattern too large"); m.M_i[nM] = i; m.M_j[nM] = j; ++nM; }
   m.nM = nM;

@@ -15,6 +15,7 @@ constexpr int MAXEQ = 3;     // equality constraints
 constexpr int MAXSITE = 4;   // tracked sites (tcp, handle, pad)
 constexpr int MAXNM = 128;   // nnz of lower-triangular M
 constexpr int MAXKEY = 2;
+constexpr int MAXANC = 12;    // ancestors of a dof in the dof tree
 constexpr int MAXCON = 32;   // contacts per env
 constexpr int MAXEFC = 112;  // constraint rows per env
 
@@ -51,6 +52,7 @@ struct DevModel {
   int dof_body[MAXV], dof_parent[MAXV], dof_qadr[MAXV], dof_limited[MAXV], dof_free_k[MAXV];  // free_k: -1 hinge, 0..5 component of a free joint
   Real dof_armature[MAXV], dof_damping[MAXV], dof_frictionloss[MAXV], dof_invw[MAXV], dof_stiffness[MAXV], dof_springref[MAXV];
   Real dof_range[MAXV][2], dof_margin[MAXV], dof_lim_solref[MAXV][2], dof_lim_solimp[MAXV][5], dof_fl_solref[MAXV][2], dof_fl_solimp[MAXV][5];
+  int dof_nanc[MAXV], dof_anc[MAXV][MAXANC], max_nanc;   // dof-tree ancestors, nearest first (sparse L^T D L of the Euler solve)
   int fl_dof[MAXV];  // dofs with frictionloss, in order
   int dof_flrow[MAXV];  // position of the dof in fl_dof, -1 when it has no friction loss
   // lower-triangular sparsity of M: (i, j) with j ancestor-or-self of i

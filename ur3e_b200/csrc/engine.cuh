@@ -1011,19 +1011,66 @@ UR3E_PHASE void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
 
 template <typename Real> UR3E_HD int is_bad(Real x) { return !(x == x) || x > Real(1e10) || x < Real(-1e10); }
 
+// ---------------------------------------------------------------- tree-sparse solve for the Euler step
+// (M + h diag(damping)) x = b.  M has the sparsity of the dof tree, so the reverse-order L^T D L factorisation has no
+// fill-in (the scheme MuJoCo uses for mj_factorM): processing dof k only touches the entries between its ancestors.
+// A = packed lower triangle (i(i+1)/2 + j) held in the Newton matrix storage; x in shared memory.
+template <typename Real, typename D>
+UR3E_PHASE void tree_ldl_solve(const DevModel<Real>& m, Arena<Real, D>& s, Real* x) {
+  const int nv = m.nv;
+  Real* A = &s.fr.n.H[0][0];
+#pragma unroll 1
+  for (int k = nv - 1; k > 0; --k) {
+    const int na = m.dof_nanc[k];
+    if (na == 0) continue;
+    const Real* rk = A + k * (k + 1) / 2;
+    const Real inv = Real(1) / rk[k];
+    WARP_FOR(e, na * (na + 1) / 2) {
+      const int pq = m.tri_ab[e], i = m.dof_anc[k][pq & 255], j = m.dof_anc[k][pq >> 8];   // j <= i, both ancestors of k
+      A[i * (i + 1) / 2 + j] -= rk[i] * rk[j] * inv;
+    }
+    WARP_SYNC();
+  }
+  WARP_FOR(k, nv) s.dinv[k] = Real(1) / A[k * (k + 1) / 2 + k];
+  WARP_SYNC();
+  // x <- L^-T x  (unit L, L[k][i] = A[k][i] / A[k][k])
+#pragma unroll 1
+  for (int k = nv - 1; k > 0; --k) {
+    const int na = m.dof_nanc[k];
+    if (na == 0) continue;
+    const Real* rk = A + k * (k + 1) / 2;
+    const Real xk = x[k] * s.dinv[k];
+    WARP_FOR(t, na) { const int i = m.dof_anc[k][t]; x[i] -= rk[i] * xk; }
+    WARP_SYNC();
+  }
+  WARP_FOR(k, nv) x[k] *= s.dinv[k];
+  WARP_SYNC();
+  // x <- L^-1 x, level by level down the dof tree
+#pragma unroll 1
+  for (int dep = 1; dep <= m.max_nanc; ++dep) {
+    WARP_FOR(k, nv) {
+      if (m.dof_nanc[k] == dep) {
+        const Real* rk = A + k * (k + 1) / 2;
+        Real v = 0;
+        for (int t = 0; t < dep; ++t) { const int i = m.dof_anc[k][t]; v += rk[i] * x[i]; }
+        x[k] -= v * s.dinv[k];
+      }
+    }
+    WARP_SYNC();
+  }
+}
+
 template <typename Real, typename D>
 UR3E_PHASE void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nv = m.nv; const Real h = m.timestep;
   Real* qa = s.qacc;
   if (m.has_damping) {
     // (M + h diag(damping)) a = qfrc_smooth + qfrc_constraint   
-    WARP_FOR(i, nv * (nv + 1)) {
-      int r = i / nv, c = i - r * nv;
-      if (r < nv) { if (c <= r) s.fr.n.H[r][c] = s.M[r * (r + 1) / 2 + c] + (r == c ? h * m.dof_damping[r] : Real(0)); }
-      else s.fr.n.H[r][c] = s.qfrc_smooth[c] + s.qfrc_constraint[c];
-    }
+    Real* A = &s.fr.n.H[0][0];
+    WARP_FOR(e, nv * (nv + 1) / 2) { const int ab = m.tri_ab[e]; A[e] = s.M[e] + ((ab >> 8) == (ab & 255) ? h * m.dof_damping[ab >> 8] : Real(0)); }
+    WARP_FOR(d, nv) s.search[d] = s.qfrc_smooth[d] + s.qfrc_constraint[d];
     WARP_SYNC();
-    chol_solve_aug(s, nv, s.search);
+    tree_ldl_solve(m, s, s.search);
     qa = s.search;
   }
   WARP_FOR(d, nv) s.st.qvel[d] += h * qa[d];
