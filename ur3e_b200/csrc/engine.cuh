@@ -17,17 +17,20 @@ struct Dims {
   static constexpr int MAXCON = MAXCON_ > 0 ? MAXCON_ : 1, MAXEFC = MAXEFC_ > 0 ? MAXEFC_ : 1;
   static constexpr bool HAS_CONTACT = MAXCON_ > 0;
   static constexpr int NS = MAXSITE;
-  static constexpr int HS = ((NV_ + 1) | 1);   // odd row stride: one row per lane is conflict-free
   static constexpr int NGRP = MAXEQ + NPAIR;
+  static constexpr int MAXDENSE = HAS_CONTACT ? 3 * MAXEQ + 3 * MAXCON : 1;   // stored Jacobian rows
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // body counts are after fixed-body merging (merge_bodies.h)          // assets/ur3e_raw.xml
 using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 16, 64>;    // assets/ur3e_2f85.xml
 using DimsMain = Dims<19, 20, 21, 7, 7, 13, 24, 96>;   // assets/main.xml
-using DimsMainLite = Dims<19, 20, 21, 7, 7, 13, 8, 40>;   // same model, caps for the common case (<= 8 contacts, <= 40 rows)
+using DimsMainLite = Dims<19, 20, 21, 7, 7, 13, 8, 48>;   // same model, caps for the common case (<= 8 contacts, <= 48 rows)
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
+constexpr int STAGE_W = 3 + 4 * STAGE_PTS;
 
-enum RowType { ROW_EQ = 0, ROW_FRICTION = 1, ROW_LIMIT = 2, ROW_CON_N = 3, ROW_CON_T1 = 4, ROW_CON_T2 = 5 };
+// row kinds; the rows of a launch are ordered [connect equalities | contacts] (dense: these have a stored Jacobian row)
+// then [joint equalities | friction loss | joint limits] (sparse: one or two +-1 / polynomial entries, never stored)
+enum RowType { ROW_EQ = 0, ROW_EQJ = 1, ROW_FRICTION = 2, ROW_LIMIT_LO = 3, ROW_LIMIT_HI = 4, ROW_CON_N = 5, ROW_CON_T1 = 6, ROW_CON_T2 = 7 };
 
 // Persistent per-environment record (lives in HBM between launches, one contiguous 16-byte aligned block per
 // environment so that a warp loads/stores it with coalesced 128-bit accesses).
@@ -50,7 +53,7 @@ struct Arena {
   Real xpos[D::NB][3];
   union {   // body frames are dead once the constraint rows exist; the Newton / Euler matrix reuses their storage
     struct { Real xquat[D::NB][4], xmat[D::NB][9], xipos[D::NB][3]; } k;
-    struct { alignas(16) Real H[D::NV + 1][D::HS]; } n;   // rows padded to a multiple of 4
+    struct { Real H[(D::NV + 1) * (D::NV + 2) / 2]; } n;   // augmented Newton / Euler matrix, packed lower triangle: (i,j) at i(i+1)/2 + j
   } fr;
   union { alignas(16) Real colbuf[2][32]; Real obs[32]; };   // solver scratch / the step's observation (written after the last solve)
   Real dinv[D::NV];
@@ -67,11 +70,16 @@ struct Arena {
   int grp_mask[D::NGRP];
   uint8_t grp_row0[D::NGRP], grp_nrow[D::NGRP];
   uint8_t stage_n[D::NPAIR], stage_off[D::NPAIR];
+  Real eqj_deriv[MAXEQ];
+  // per dof: its sparse rows (255 = none) so that the solver's inner loops never touch the model tables
+  Real sp_ejc[D::NV];
+  uint8_t sp_fl[D::NV], sp_lo[D::NV], sp_hi[D::NV], sp_ej[D::NV];
+  int nd, rf0, rl0;   // dense rows [0, nd); friction rows from rf0, limit rows from rl0
   int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
   union {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
-    Real stage[D::NPAIR][STAGE_PTS][7];  // pos 3, normal 3, dist
-    Real efc_J[D::MAXEFC][D::NV];
+    Real stage[D::NPAIR][STAGE_W];   // per candidate pair: shared normal (3), then up to STAGE_PTS x (pos 3, dist 1)
+    Real efc_J[D::MAXDENSE][D::NV];   // dense rows only
   } u;
 };
 
@@ -375,7 +383,7 @@ template <typename Real> UR3E_HD void make_frame(Real* f) {
 }
 
 template <typename Real>
-UR3E_PHASE int plane_box(const Real* ppos, const Real* pmat, const Real* bpos, const Real* bmat, const Real* size, Real margin, Real (*out)[7]) {
+UR3E_PHASE int plane_box(const Real* ppos, const Real* pmat, const Real* bpos, const Real* bmat, const Real* size, Real margin, Real* out) {
   Real n[3] = {pmat[2], pmat[5], pmat[8]};
   Real dif[3] = {bpos[0] - ppos[0], bpos[1] - ppos[1], bpos[2] - ppos[2]};
   Real cd = dot3(dif, n);
@@ -386,8 +394,8 @@ UR3E_PHASE int plane_box(const Real* ppos, const Real* pmat, const Real* bpos, c
     Real ld = dot3(n, c);
     if (cd + ld > margin || ld > 0) continue;
     Real dist = cd + ld;
-    for (int k = 0; k < 3; ++k) { out[cnt][k] = c[k] + bpos[k] - n[k] * dist * Real(0.5); out[cnt][3 + k] = n[k]; }
-    out[cnt][6] = dist;
+    for (int k = 0; k < 3; ++k) { out[3 + 4 * cnt + k] = c[k] + bpos[k] - n[k] * dist * Real(0.5); out[k] = n[k]; }
+    out[3 + 4 * cnt + 3] = dist;
     if (++cnt >= 4) break;
   }
   return cnt;
@@ -409,7 +417,7 @@ UR3E_HD int clip_poly(Real* px, Real* py, int n, Real a, Real b, Real c) {
 
 // box-box manifold; same rules as the oracle's box_box (oracle/ur3e_oracle.c), normal from box 1 to box 2
 template <typename Real>
-UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Real* p2, const Real* R2, const Real* s2, Real margin, Real (*out)[7]) {
+UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Real* p2, const Real* R2, const Real* s2, Real margin, Real* out) {
   Real d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, A1[3][3], A2[3][3];
   for (int i = 0; i < 3; ++i) for (int k = 0; k < 3; ++k) { A1[i][k] = R1[3 * k + i]; A2[i][k] = R2[3 * k + i]; }
   Real AC[3][3];
@@ -448,8 +456,8 @@ UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Rea
     Real b = dot3(u, v), dd = dot3(u, w), e = dot3(v, w), den = 1 - b * b;
     Real sa = (b * e - dd) / den, sb = (e - b * dd) / den;
     sa = rmin(rmax(sa, -s1[ei]), s1[ei]); sb = rmin(rmax(sb, -s2[ej]), s2[ej]);
-    for (int k = 0; k < 3; ++k) { out[0][k] = Real(0.5) * (c1[k] + sa * u[k] + c2[k] + sb * v[k]); out[0][3 + k] = en[k]; }
-    out[0][6] = ebest;
+    for (int k = 0; k < 3; ++k) { out[3 + k] = Real(0.5) * (c1[k] + sa * u[k] + c2[k] + sb * v[k]); out[k] = en[k]; }
+    out[6] = ebest;
     return 1;
   }
   bool ref1 = code < 3; int ra = ref1 ? code : code - 3;
@@ -479,8 +487,8 @@ UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Rea
     for (int k = 0; k < 3; ++k) { base[k] = rc[k] + px[c] * RA[ru][k] + py[c] * RA[rv][k]; r[k] = fc[k] - base[k]; }
     Real h = Num<Real>::abs(nn) > Real(1e-12) ? dot3(ni, r) / nn : Real(0);
     if (h > margin) continue;
-    for (int k = 0; k < 3; ++k) { out[cnt][k] = base[k] + Real(0.5) * h * nref[k]; out[cnt][3 + k] = bn[k]; }
-    out[cnt][6] = h;
+    for (int k = 0; k < 3; ++k) { out[3 + 4 * cnt + k] = base[k] + Real(0.5) * h * nref[k]; out[k] = bn[k]; }
+    out[3 + 4 * cnt + 3] = h;
     ++cnt;
   }
   return cnt;
@@ -504,7 +512,8 @@ UR3E_PHASE void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
         if (dot3(dd, dd) <= r * r) n = box_box(x1, s.geom_xmat[g1], m.geom_size[g1], x2, s.geom_xmat[g2], m.geom_size[g2], margin, s.u.stage[p]);
       }
       int keep = 0;   // MuJoCo keeps a contact only when dist < margin
-      for (int c = 0; c < n; ++c) if (s.u.stage[p][c][6] < margin) { if (keep != c) for (int k = 0; k < 7; ++k) s.u.stage[p][keep][k] = s.u.stage[p][c][k]; ++keep; }
+      Real* st = s.u.stage[p];
+      for (int c = 0; c < n; ++c) if (st[3 + 4 * c + 3] < margin) { if (keep != c) for (int k = 0; k < 4; ++k) st[3 + 4 * keep + k] = st[3 + 4 * c + k]; ++keep; }
       s.stage_n[p] = (uint8_t)keep;
     }
     WARP_SYNC();
@@ -518,9 +527,9 @@ UR3E_PHASE void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
       int p = i / STAGE_PTS, c = i % STAGE_PTS;
       int o = s.stage_off[p] + c;
       if (c < s.stage_n[p] && o < capc) {
-        const Real* src = s.u.stage[p][c];
-        for (int k = 0; k < 3; ++k) { s.con_pos[o][k] = src[k]; s.cu.frame[o][k] = src[3 + k]; }
-        s.con_dist[o] = src[6]; s.con_pair[o] = (uint8_t)p;
+        const Real* src = s.u.stage[p];
+        for (int k = 0; k < 3; ++k) { s.con_pos[o][k] = src[3 + 4 * c + k]; s.cu.frame[o][k] = src[k]; }
+        s.con_dist[o] = src[3 + 4 * c + 3]; s.con_pair[o] = (uint8_t)p;
         make_frame(s.cu.frame[o]);
       }
     }
@@ -562,12 +571,33 @@ template <typename Real> UR3E_HD void kb_params(const Real* solref, const Real* 
   } else { *K = -solref[0] / rmax(Num<Real>::minval, dmax * dmax); *B = -solref[1] / rmax(Num<Real>::minval, dmax); }
 }
 
+// J[r] . x for any row (dense rows read the stored Jacobian, sparse rows are one or two entries)
+template <typename Real, typename D>
+UR3E_HD Real row_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int r, const Real* x) {
+  if (r < s.nd) { const Real* J = s.u.efc_J[r]; Real v = 0; for (int k = 0; k < m.nv; ++k) v += J[k] * x[k]; return v; }
+  const int t = s.efc_type[r], id = s.efc_id[r];
+  if (t == ROW_EQJ) { const int d2 = m.eq_o2[id]; Real v = x[m.eq_o1[id]]; if (d2 >= 0) v -= s.eqj_deriv[id] * x[d2]; return v; }
+  return t == ROW_LIMIT_HI ? -x[id] : x[id];
+}
+// sum_r J[r][d] f[r] over all rows
+template <typename Real, typename D>
+UR3E_HD Real col_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int d, const Real* f) {
+  (void)m;
+  Real v = 0;
+  for (int r = 0; r < s.nd; ++r) v += s.u.efc_J[r][d] * f[r];
+  int r = s.sp_ej[d]; if (r != 255) v += s.sp_ejc[d] * f[r];
+  r = s.sp_fl[d]; if (r != 255) v += f[r];
+  r = s.sp_lo[d]; if (r != 255) v += f[r];
+  r = s.sp_hi[d]; if (r != 255) v -= f[r];
+  return v;
+}
+
 template <typename Real, typename D>
 UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nv = m.nv;
-  // row budget: equality, friction loss (static), limits (dynamic), contacts (3 rows each)
-  int ne = 0;
-  for (int e = 0; e < m.neq; ++e) ne += m.eq_kind[e] == EK_CONNECT ? 3 : 1;
+  // row budget: dense rows = connect equalities + contacts (3 rows each), sparse rows = joint equalities, friction loss, limits
+  int ndeq = 0, nej = 0;
+  for (int e = 0; e < m.neq; ++e) { if (m.eq_kind[e] == EK_CONNECT) ndeq += 3; else nej += 1; }
   const int nf = m.nfl;
   int mlo = 0, mhi = 0;   // bit d: lower / upper limit of dof d is active (dist < margin)
   WARP_FOR(d, nv) {
@@ -578,21 +608,27 @@ UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
     }
   }
   mlo = warp_or(mlo); mhi = warp_or(mhi);
-  const int nl = popcount32(mlo) + popcount32(mhi);
-  int base_c = ne + nf + nl;
-  int ncon = s.ncon;
+  int nl = popcount32(mlo) + popcount32(mhi);
   const int cape = s.cap_efc;   // <= D::MAXEFC
-  if (base_c + 3 * ncon > cape) { ncon = (cape - base_c) / 3; if (ncon < 0) ncon = 0; IF_LANE0 { s.overflow |= 2; s.ncon = ncon; } }
-  int nefc = base_c + 3 * ncon; if (nefc > cape) nefc = cape;
-  // row groups: rows that share one column set (used by the Hessian assembly)
+  int ncon = s.ncon;
+  {
+    int room = cape - ndeq - nej - nf - nl, roomd = D::MAXDENSE - ndeq;
+    if (room < 0) { room = 0; }
+    int cmax = (room < roomd ? room : roomd) / 3;
+    if (cmax < 0) cmax = 0;
+    if (ncon > cmax) { ncon = cmax; IF_LANE0 { s.overflow |= 2; s.ncon = ncon; } }
+  }
+  const int base_c = ndeq, nd = ndeq + 3 * ncon, rej0 = nd, rf0 = nd + nej, rl0 = rf0 + nf;
+  int nefc = rl0 + nl;
+  if (nefc > cape) { nefc = cape; IF_LANE0 s.overflow |= 2; }
+  // row groups: dense rows that share one column set (used by the Hessian assembly)
   int ngrp = 0;
   {
     int row = 0;
-    for (int e = 0; e < m.neq; ++e) {
-      const bool con = m.eq_kind[e] == EK_CONNECT;
-      const int mask = con ? (int)(m.body_dofmask[m.eq_o1[e]] | m.body_dofmask[m.eq_o2[e]]) : ((1 << m.eq_o1[e]) | (m.eq_o2[e] >= 0 ? (1 << m.eq_o2[e]) : 0));
-      IF_LANE0 { s.grp_row0[ngrp] = (uint8_t)row; s.grp_nrow[ngrp] = con ? 3 : 1; s.grp_mask[ngrp] = mask; }
-      ++ngrp; row += con ? 3 : 1;
+    for (int e = 0; e < m.neq; ++e) if (m.eq_kind[e] == EK_CONNECT) {
+      const int mask = (int)(m.body_dofmask[m.eq_o1[e]] | m.body_dofmask[m.eq_o2[e]]);
+      IF_LANE0 { s.grp_row0[ngrp] = (uint8_t)row; s.grp_nrow[ngrp] = 3; s.grp_mask[ngrp] = mask; }
+      ++ngrp; row += 3;
     }
     if constexpr (D::HAS_CONTACT) {
       int prev = -1;
@@ -607,12 +643,20 @@ UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
       }
     }
   }
-  IF_LANE0 { s.ne = ne; s.nf = nf; s.nl = nl; s.nefc = nefc; s.ngrp = ngrp; s.lim_lo = mlo; s.lim_hi = mhi; }
-  WARP_FOR(i, nefc * nv) (&s.u.efc_J[0][0])[i] = 0;
+  IF_LANE0 { s.ne = ndeq + nej; s.nf = nf; s.nl = nl; s.nefc = nefc; s.ngrp = ngrp; s.lim_lo = mlo; s.lim_hi = mhi; s.nd = nd; s.rf0 = rf0; s.rl0 = rl0; }
+  WARP_FOR(d, nv) {
+    const int k = m.dof_flrow[d], below = (1 << d) - 1;
+    int r = rl0 + popcount32(mlo & below) + popcount32(mhi & below);
+    s.sp_fl[d] = (uint8_t)((k >= 0 && rf0 + k < nefc) ? rf0 + k : 255);
+    s.sp_lo[d] = (uint8_t)((((mlo >> d) & 1) && r < nefc) ? r : 255);
+    if ((mlo >> d) & 1) ++r;
+    s.sp_hi[d] = (uint8_t)((((mhi >> d) & 1) && r < nefc) ? r : 255);
+    s.sp_ej[d] = 255; s.sp_ejc[d] = 0;
+  }
   WARP_SYNC();
-  // equality rows; efc_aref temporarily holds pos, efc_jv holds margin
+  // rows: efc_aref temporarily holds pos, efc_jv holds margin
   {
-    int row = 0;
+    int row = 0, rj = rej0;
     for (int e = 0; e < m.neq; ++e) {
       if (m.eq_kind[e] == EK_CONNECT) {
         int b1 = m.eq_o1[e], b2 = m.eq_o2[e];
@@ -634,30 +678,29 @@ UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
             Real p2 = s.st.qpos[m.dof_qadr[d2]] - m.qpos0[m.dof_qadr[d2]];
             pos = p1 - (c[0] + p2 * (c[1] + p2 * (c[2] + p2 * (c[3] + p2 * c[4]))));
             deriv = c[1] + p2 * (2 * c[2] + p2 * (3 * c[3] + p2 * 4 * c[4]));
-            s.u.efc_J[row][d2] = -deriv;
           } else pos = p1 - c[0];
-          s.u.efc_J[row][d1] = 1;
-          s.efc_aref[row] = pos; s.efc_jv[row] = 0; s.efc_type[row] = ROW_EQ; s.efc_id[row] = (uint8_t)e;
+          s.eqj_deriv[e] = deriv;
+          if (rj < nefc) { s.sp_ej[d1] = (uint8_t)rj; s.sp_ejc[d1] = 1; if (d2 >= 0) { s.sp_ej[d2] = (uint8_t)rj; s.sp_ejc[d2] = -deriv; } }
+          if (rj < D::MAXEFC) { s.efc_aref[rj] = pos; s.efc_jv[rj] = 0; s.efc_type[rj] = ROW_EQJ; s.efc_id[rj] = (uint8_t)e; }
         }
-        row += 1;
+        rj += 1;
       }
     }
   }
   WARP_FOR(k, nf) {
-    int d = m.fl_dof[k], r = ne + k;
-    s.u.efc_J[r][d] = 1; s.efc_aref[r] = 0; s.efc_jv[r] = 0; s.efc_type[r] = ROW_FRICTION; s.efc_id[r] = (uint8_t)d;
+    int d = m.fl_dof[k], r = rf0 + k;
+    if (r < D::MAXEFC) { s.efc_aref[r] = 0; s.efc_jv[r] = 0; s.efc_type[r] = ROW_FRICTION; s.efc_id[r] = (uint8_t)d; }
   }
   WARP_FOR(i, 2 * nv) {
     int d = i >> 1, k = i & 1;
     int active = ((k == 0 ? mlo : mhi) >> d) & 1;
     if (active) {
       int below = (1 << d) - 1;
-      int r = ne + nf + popcount32(mlo & below) + popcount32(mhi & below) + (k == 1 ? ((mlo >> d) & 1) : 0);
+      int r = rl0 + popcount32(mlo & below) + popcount32(mhi & below) + (k == 1 ? ((mlo >> d) & 1) : 0);
       if (r < D::MAXEFC) {
         Real q = s.st.qpos[m.dof_qadr[d]];
-        s.u.efc_J[r][d] = k == 0 ? Real(1) : Real(-1);
         s.efc_aref[r] = k == 0 ? q - m.dof_range[d][0] : m.dof_range[d][1] - q;
-        s.efc_jv[r] = m.dof_margin[d]; s.efc_type[r] = ROW_LIMIT; s.efc_id[r] = (uint8_t)d;
+        s.efc_jv[r] = m.dof_margin[d]; s.efc_type[r] = k == 0 ? ROW_LIMIT_LO : ROW_LIMIT_HI; s.efc_id[r] = (uint8_t)d;
       }
     }
   }
@@ -683,9 +726,9 @@ UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
     int t = s.efc_type[r], id = s.efc_id[r];
     Real pos = s.efc_aref[r], margin = s.efc_jv[r];
     const Real *solref, *solimp; Real diag; bool fric = false;
-    if (t == ROW_EQ) { solref = m.eq_solref[id]; solimp = m.eq_solimp[id]; diag = m.eq_invw[id]; }
+    if (t == ROW_EQ || t == ROW_EQJ) { solref = m.eq_solref[id]; solimp = m.eq_solimp[id]; diag = m.eq_invw[id]; }
     else if (t == ROW_FRICTION) { solref = m.dof_fl_solref[id]; solimp = m.dof_fl_solimp[id]; diag = m.dof_invw[id]; fric = true; }
-    else if (t == ROW_LIMIT) { solref = m.dof_lim_solref[id]; solimp = m.dof_lim_solimp[id]; diag = m.dof_invw[id]; }
+    else if (t == ROW_LIMIT_LO || t == ROW_LIMIT_HI) { solref = m.dof_lim_solref[id]; solimp = m.dof_lim_solimp[id]; diag = m.dof_invw[id]; }
     else {
       int p = s.con_pair[id]; solref = m.pair_solref[p]; solimp = m.pair_solimp[p]; diag = m.pair_invw[p];
       if (t != ROW_CON_N) { fric = true; pos = 0; margin = 0; }
@@ -704,7 +747,7 @@ UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
       else R = R1 * m.pair_friction[p][0] * m.pair_friction[p][0] / (m.pair_friction[p][1] * m.pair_friction[p][1]);
     }
     if (fric) K = 0;
-    Real vel = 0; for (int k = 0; k < nv; ++k) vel += s.u.efc_J[r][k] * s.st.qvel[k];
+    const Real vel = row_dot(m, s, r, s.st.qvel);
     s.efc_D[r] = 1 / R;
     s.efc_aref[r] = -B * vel - K * imp * (pos - margin);
   }
@@ -712,7 +755,8 @@ UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
 }
 
 // ---------------------------------------------------------------- dense SPD solve on the augmented matrix
-// Input: lower triangle of s.fr.n.H, rows 0..n-1 = SPD matrix, row n = right-hand side.  Output x[0..n) (shared memory).
+// Input: packed lower triangle s.fr.n.H (row i at i(i+1)/2; triangular offsets mod 32 are distinct, so one row per lane is
+// bank-conflict free), rows 0..n-1 = SPD matrix, row n = right-hand side.  Output x[0..n) (shared memory).
 // Right-looking Cholesky with one row per lane: at step k lane i (> k) scales its entry of column k and applies the
 // rank-1 update to its own row, reading the raw column k as warp-wide broadcasts; one __syncwarp per step.  Loops are
 // deliberately kept rolled: the step's code has to stay resident in the SM's 32 KB instruction cache (profiles/r1_summary.md).
@@ -723,21 +767,22 @@ UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
   // Factor (unscaled) with the forward substitution folded in: after step k, raw[i][k] = L[i][k] * L[k][k] and the
   // right-hand side (kept in y) has had column k eliminated.  Exact zeros (block / tree sparsity of M + J^T D J) are skipped.
   Real* y = s.colbuf[0];
-  WARP_FOR(k, n) y[k] = s.fr.n.H[n][k];
+  Real* const A = s.fr.n.H;
+  WARP_FOR(k, n) y[k] = A[n * (n + 1) / 2 + k];
   WARP_SYNC();
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
-    Real d = s.fr.n.H[k][k];
+    Real d = A[k * (k + 1) / 2 + k];
     d = d > Num<Real>::minval ? d : Num<Real>::minval;
     const Real inv = Real(1) / d, yk = y[k];
     WARP_FOR(i, n) {
       if (i > k) {
-        Real* row = s.fr.n.H[i];
+        Real* row = A + i * (i + 1) / 2;
         const Real t = row[k] * inv;
         if (t != 0) {
           y[i] -= t * yk;
 #pragma unroll 4
-          for (int j = k + 1; j <= i; ++j) row[j] -= t * s.fr.n.H[j][k];
+          for (int j = k + 1; j <= i; ++j) row[j] -= t * A[j * (j + 1) / 2 + k];
         }
       }
     }
@@ -745,14 +790,14 @@ UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
   }
   // scale to the true factor once: L[i][k] = raw[i][k] / sqrt(d_k), z = L^-1 b, and keep 1 / L_kk
   WARP_FOR(k, n) {
-    Real d = s.fr.n.H[k][k];
+    Real d = A[k * (k + 1) / 2 + k];
     d = d > Num<Real>::minval ? d : Num<Real>::minval;
     const Real rs = Real(1) / Num<Real>::sqrt(d);
     s.dinv[k] = rs;
     y[k] *= rs;
   }
   WARP_SYNC();
-  WARP_FOR(i, n) { Real* row = s.fr.n.H[i];
+  WARP_FOR(i, n) { Real* row = A + i * (i + 1) / 2;
 #pragma unroll 4
     for (int k = 0; k < i; ++k) row[k] *= s.dinv[k]; }
   WARP_SYNC();
@@ -760,7 +805,7 @@ UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
 #pragma unroll 1
   for (int k = n - 1; k >= 0; --k) {
     const Real xk = y[k] * s.dinv[k];
-    const Real* Lk = s.fr.n.H[k];
+    const Real* Lk = A + k * (k + 1) / 2;
     WARP_FOR(i, k + 1) { if (i == k) x[i] = xk; else y[i] -= Lk[i] * xk; }
     WARP_SYNC();
   }
@@ -773,13 +818,13 @@ UR3E_PHASE void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bo
   WARP_FOR(r, s.nefc) {
     int t = s.efc_type[r];
     Real Dr = s.efc_D[r], x = s.efc_jar[r];
-    if (t == ROW_EQ) { s.efc_force[r] = -Dr * x; s.efc_Dact[r] = Dr; }
+    if (t == ROW_EQ || t == ROW_EQJ) { s.efc_force[r] = -Dr * x; s.efc_Dact[r] = Dr; }
     else if (t == ROW_FRICTION) {
       Real f = m.dof_frictionloss[s.efc_id[r]], rf = f / Dr;
       if (x <= -rf) { s.efc_force[r] = f; s.efc_Dact[r] = 0; }
       else if (x >= rf) { s.efc_force[r] = -f; s.efc_Dact[r] = 0; }
       else { s.efc_force[r] = -Dr * x; s.efc_Dact[r] = Dr; }
-    } else if (t == ROW_LIMIT) {
+    } else if (t == ROW_LIMIT_LO || t == ROW_LIMIT_HI) {
       if (x < 0) { s.efc_force[r] = -Dr * x; s.efc_Dact[r] = Dr; } else { s.efc_force[r] = 0; s.efc_Dact[r] = 0; }
     } else if (t == ROW_CON_N) {
       int c = s.efc_id[r], p = s.con_pair[c];
@@ -817,11 +862,11 @@ UR3E_PHASE void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real
   WARP_FOR(r, s.nefc) {
     int t = s.efc_type[r];
     Real Dr = s.efc_D[r], v = s.efc_jv[r], x = s.efc_jar[r] + alpha * v;
-    if (t == ROW_EQ) { p1 += Dr * x * v; p2 += Dr * v * v; }
+    if (t == ROW_EQ || t == ROW_EQJ) { p1 += Dr * x * v; p2 += Dr * v * v; }
     else if (t == ROW_FRICTION) {
       Real f = m.dof_frictionloss[s.efc_id[r]], rf = f / Dr;
       if (x <= -rf) p1 -= f * v; else if (x >= rf) p1 += f * v; else { p1 += Dr * x * v; p2 += Dr * v * v; }
-    } else if (t == ROW_LIMIT) { if (x < 0) { p1 += Dr * x * v; p2 += Dr * v * v; } }
+    } else if (t == ROW_LIMIT_LO || t == ROW_LIMIT_HI) { if (x < 0) { p1 += Dr * x * v; p2 += Dr * v * v; } }
     else if (t == ROW_CON_N) {
       int c = s.efc_id[r], p = s.con_pair[c];
       Real mu = s.con_mu[c], f1 = m.pair_friction[p][0], f2 = m.pair_friction[p][1];
@@ -853,8 +898,8 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
     constraint_update(m, s, true);
     Real gg = 0, gref = 0;
     WARP_FOR(d, nv) {
-      Real g = s.Ma[d] - s.qfrc_smooth[d], fc = 0;
-      for (int r = 0; r < nefc; ++r) fc += s.u.efc_J[r][d] * s.efc_force[r];
+      Real g = s.Ma[d] - s.qfrc_smooth[d];
+      const Real fc = col_dot(m, s, d, s.efc_force);
       g -= fc;
       s.grad[d] = g; gg += g * g; gref += s.Ma[d] * s.Ma[d] + s.qfrc_smooth[d] * s.qfrc_smooth[d] + fc * fc;
     }
@@ -864,22 +909,19 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
     // H = M + J^T diag(Dact) J + cone blocks ; augmented row = -grad.
     // phase A: M, the single-column rows (friction loss, limits) and the rhs row
     {
-      const int ne = s.ne, rl0 = s.ne + s.nf, mlo = s.lim_lo, mhi = s.lim_hi;
       WARP_FOR(e, (nv + 1) * (nv + 2) / 2) {
         int ab = m.tri_ab[e], a = ab >> 8, b = ab & 255;   // (a, b), b <= a, over the (nv+1) x (nv+1) lower triangle
-        if (a == nv) { if (b < nv) s.fr.n.H[nv][b] = -s.grad[b]; }
+        if (a == nv) { if (b < nv) s.fr.n.H[e] = -s.grad[b]; }
         else {
-          Real h = s.M[a * (a + 1) / 2 + b];
+          Real h = s.M[e];
           if (a == b) {
-            int k = m.dof_flrow[a];
-            if (k >= 0) h += s.efc_Dact[ne + k];
-            if (((mlo | mhi) >> a) & 1) {
-              int below = (1 << a) - 1, r = rl0 + popcount32(mlo & below) + popcount32(mhi & below);
-              if ((mlo >> a) & 1) { if (r < D::MAXEFC) h += s.efc_Dact[r]; ++r; }
-              if ((mhi >> a) & 1) { if (r < D::MAXEFC) h += s.efc_Dact[r]; }
-            }
+            int r = s.sp_fl[a]; if (r != 255) h += s.efc_Dact[r];
+            r = s.sp_lo[a]; if (r != 255) h += s.efc_Dact[r];
+            r = s.sp_hi[a]; if (r != 255) h += s.efc_Dact[r];
           }
-          s.fr.n.H[a][b] = h;
+          const int ra = s.sp_ej[a];   // joint equality: D [c_a c_b] on its two dofs
+          if (ra != 255 && ra == s.sp_ej[b]) h += s.efc_Dact[ra] * s.sp_ejc[a] * s.sp_ejc[b];
+          s.fr.n.H[e] = h;
         }
       }
       WARP_SYNC();
@@ -893,7 +935,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
         Real h = 0;
         if (!contact) { for (int r = r0; r < r1; ++r) h += s.efc_Dact[r] * s.u.efc_J[r][a] * s.u.efc_J[r][b]; }
         else {
-          for (int r = r0; r < r1 && r + 2 < D::MAXEFC; r += 3) {
+          for (int r = r0; r + 2 < r1 + 0 && r + 2 < D::MAXDENSE; r += 3) {
             Real a0 = s.u.efc_J[r][a], a1 = s.u.efc_J[r + 1][a], a2 = s.u.efc_J[r + 2][a];
             Real b0 = s.u.efc_J[r][b], b1 = s.u.efc_J[r + 1][b], b2 = s.u.efc_J[r + 2][b];
             const Real* Hc = s.cu.H[s.efc_id[r]];
@@ -901,7 +943,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
             else h += s.efc_Dact[r] * a0 * b0 + s.efc_Dact[r + 1] * a1 * b1 + s.efc_Dact[r + 2] * a2 * b2;
           }
         }
-        s.fr.n.H[a][b] += h;
+        s.fr.n.H[a * (a + 1) / 2 + b] += h;
       }
       WARP_SYNC();
     }
@@ -909,7 +951,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
     // Mv, jv, and the quadratic (Gauss) part of the line cost
     WARP_FOR(i, nv + nefc) {
       if (i < nv) s.Mv[i] = sym_matvec_row(s.M, s.search, i, nv);
-      else { int r = i - nv; Real v = 0; for (int k = 0; k < nv; ++k) v += s.u.efc_J[r][k] * s.search[k]; s.efc_jv[r] = v; }
+      else { int r = i - nv; s.efc_jv[r] = row_dot(m, s, r, s.search); }
     }
     WARP_SYNC();
     Real g1 = 0, g2 = 0, sn = 0, pred = 0;
@@ -947,7 +989,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
   const int nv = m.nv, nefc = s.nefc;
   if (nefc == 0) {
     // unconstrained: qacc = M^-1 qfrc_smooth
-    WARP_FOR(i, nv * (nv + 1)) { int r = i / nv, c = i - r * nv; if (r < nv) { if (c <= r) s.fr.n.H[r][c] = s.M[r * (r + 1) / 2 + c]; } else s.fr.n.H[r][c] = s.qfrc_smooth[c]; }
+    WARP_FOR(e, nv * (nv + 1) / 2 + nv) { s.fr.n.H[e] = e < nv * (nv + 1) / 2 ? s.M[e] : s.qfrc_smooth[e - nv * (nv + 1) / 2]; }
     WARP_FOR(d, nv) s.qfrc_constraint[d] = 0;
     WARP_SYNC();
     chol_solve_aug(s, nv, s.qacc);
@@ -961,7 +1003,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
   WARP_SYNC();
   WARP_FOR(i, nv + nefc) {
     if (i < nv) s.Ma[i] = sym_matvec_row(s.M, s.qacc, i, nv);
-    else { int r = i - nv; Real v = -s.efc_aref[r]; for (int k = 0; k < nv; ++k) v += s.u.efc_J[r][k] * s.qacc[k]; s.efc_jar[r] = v; }
+    else { int r = i - nv; s.efc_jar[r] = row_dot(m, s, r, s.qacc) - s.efc_aref[r]; }
   }
   WARP_SYNC();
   // Newton iterations.  In the aligned (regular substep) case the block's warps iterate in lock-step: a converged warp
@@ -977,7 +1019,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
     }
   }
   constraint_update(m, s, false);
-  WARP_FOR(d, nv) { Real v = 0; for (int r = 0; r < nefc; ++r) v += s.u.efc_J[r][d] * s.efc_force[r]; s.qfrc_constraint[d] = v; }
+  WARP_FOR(d, nv) s.qfrc_constraint[d] = col_dot(m, s, d, s.efc_force);
   IF_LANE0 s.solver_iter = iter;
   WARP_SYNC();
 }
@@ -1018,7 +1060,7 @@ template <typename Real> UR3E_HD int is_bad(Real x) { return !(x == x) || x > Re
 template <typename Real, typename D>
 UR3E_PHASE void tree_ldl_solve(const DevModel<Real>& m, Arena<Real, D>& s, Real* x) {
   const int nv = m.nv;
-  Real* A = &s.fr.n.H[0][0];
+  Real* A = s.fr.n.H;
 #pragma unroll 1
   for (int k = nv - 1; k > 0; --k) {
     const int na = m.dof_nanc[k];
@@ -1066,7 +1108,7 @@ UR3E_PHASE void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
   Real* qa = s.qacc;
   if (m.has_damping) {
     // (M + h diag(damping)) a = qfrc_smooth + qfrc_constraint   
-    Real* A = &s.fr.n.H[0][0];
+    Real* A = s.fr.n.H;
     WARP_FOR(e, nv * (nv + 1) / 2) { const int ab = m.tri_ab[e]; A[e] = s.M[e] + ((ab >> 8) == (ab & 255) ? h * m.dof_damping[ab >> 8] : Real(0)); }
     WARP_FOR(d, nv) s.search[d] = s.qfrc_smooth[d] + s.qfrc_constraint[d];
     WARP_SYNC();
