@@ -180,3 +180,54 @@ def test_host_entry_point(assets):
     obs = np.zeros((n, 24), np.float32); rew = np.zeros(n, np.float32); te = np.zeros(n, np.uint8); tr = np.zeros(n, np.uint8)
     b.step_host(a, obs, rew, te, tr)
     assert np.isfinite(obs).all() and np.abs(obs[:, :3] - o0[:, :3]).max() < 1e-2
+
+
+def test_bad_state_autoreset_and_masked_reset(assets):
+    """mj_checkPos/Vel autoreset (MUJOCO_LOG.TXT): an environment with NaN / huge state is reset to qpos0 inside the
+    step and counted; the others are untouched.  Masked reset only touches the selected environments."""
+    n = 16
+    b = make(assets, "main.xml", n, torch.float32, ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2,
+             reset_key=1, term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500)
+    o0 = b.reset(seed=5).clone()
+    qpos, qvel, _ = b.get_state()
+    q2 = qpos.clone(); v2 = qvel.clone()
+    v2[3, 2] = float("nan"); v2[7, 0] = 1e12
+    b.set_state(q2, v2)
+    a = torch.cat([o0[:, 0:3], torch.zeros(n, 1, device="cuda")], 1).contiguous()
+    obs, rew, term, trunc = b.step(a)
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    st = b.stats_dict()
+    assert st["unstable_resets"] == 2
+    qp, qv, _ = b.get_state()
+    assert torch.isfinite(qp).all() and torch.isfinite(qv).all()
+    good = [i for i in range(n) if i not in (3, 7)]
+    assert (qp[good] - qpos[good]).abs().max() < 1e-2                 # healthy environments moved by one small step only
+    assert (qp[3, :6]).abs().max() < 0.05 and (qp[7, :6]).abs().max() < 0.05   # mj_resetData: back at qpos0 (arm joints 0), then one step
+    # masked reset
+    for _ in range(20):
+        b.step(a)
+    before, _, _ = b.get_state()
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda"); mask[2] = 1; mask[9] = 1
+    b.reset(seed=5, mask=mask)
+    after, _, _ = b.get_state()
+    keep = [i for i in range(n) if i not in (2, 9)]
+    assert torch.equal(after[keep], before[keep])
+    assert (after[2, :14] - qpos[2, :14]).abs().max() < 1e-6 and (after[9, :14] - qpos[9, :14]).abs().max() < 1e-6
+
+
+def test_state_roundtrip_and_determinism(assets):
+    """get_state -> set_state reproduces the trajectory bit for bit (the stale-kinematics cache is rebuilt by the forward pass of
+    set_state exactly as MujocoEnv.set_state does), and two batches with the same seed agree bitwise."""
+    n = 32
+    mk = lambda: make(assets, "main.xml", n, torch.float32, ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2,
+                      reset_key=1, term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500, auto_reset=1, reset_noise=lib.NOISE_HIGH)
+    b1, b2 = mk(), mk()
+    o1 = b1.reset(seed=11).clone(); o2 = b2.reset(seed=11).clone()
+    assert torch.equal(o1, o2)
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    for k in range(30):
+        a = (o1[:, 0:4] + 0.02 * torch.randn(n, 4, device="cuda", generator=g)).contiguous(); a[:, 3] = 0.5
+        x1 = b1.step(a)[0].clone(); x2 = b2.step(a)[0].clone()
+        assert torch.equal(x1, x2)
+    o3 = b2.reset(seed=12)
+    assert not torch.equal(o3[:, 3:5], o2[:, 3:5])                    # a different seed draws different mug positions
