@@ -770,19 +770,25 @@ UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
   Real* const A = s.fr.n.H;
   WARP_FOR(k, n) y[k] = A[n * (n + 1) / 2 + k];
   WARP_SYNC();
+  // the longest rows get a second lane: rows n-nh .. n-1 are updated by two lanes, each taking half of the column range
+  const int nh = n > 8 ? ((n - 8) < (32 - n) ? (n - 8) : (32 - n)) : 0;
 #pragma unroll 1
   for (int k = 0; k < n; ++k) {
     Real d = A[k * (k + 1) / 2 + k];
     d = d > Num<Real>::minval ? d : Num<Real>::minval;
     const Real inv = Real(1) / d, yk = y[k];
-    WARP_FOR(i, n) {
+    WARP_FOR(it, n + nh) {
+      const bool helper = it >= n;
+      const int i = helper ? (n - nh) + (it - n) : it;
       if (i > k) {
         Real* row = A + i * (i + 1) / 2;
         const Real t = row[k] * inv;
         if (t != 0) {
-          y[i] -= t * yk;
+          int lo = k + 1, hi = i;
+          if (i >= n - nh) { const int mid = (lo + hi) >> 1; if (helper) lo = mid + 1; else hi = mid; }
+          if (!helper) y[i] -= t * yk;
 #pragma unroll 4
-          for (int j = k + 1; j <= i; ++j) row[j] -= t * A[j * (j + 1) / 2 + k];
+          for (int j = lo; j <= hi; ++j) row[j] -= t * A[j * (j + 1) / 2 + k];
         }
       }
     }
