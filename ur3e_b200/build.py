@@ -16,6 +16,7 @@ LIB = os.path.join(HERE, "libur3e_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + ARCH
+FLAGS += os.environ.get("UR3E_EXTRA_FLAGS", "").split()   # A/B experiments only (e.g. -DUR3E_REG_CHOL=0); part of the object digest
 # float32 production units: approximate division / sqrt (2 ulp) and flush-to-zero; sin/cos stay exact. float64 validation units keep IEEE.
 F32_FLAGS = ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]
 UNITS = ["capi.cu", "mjcf.cpp"] + ["inst_%s_%s.cu" % (r, d) for r in ("f32", "f64") for d in ("raw", "grip", "main")]

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
 // The step path.  One warp per environment; the block's warps pass the substep phases together (block barriers), so every
 // warp of the block runs the same trip count: a warp without work repeats the last environment and does not store.
 template <typename Real, typename D>
-__global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) step_kernel(const KArgs<Real> a) {
+__global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_PER_SM) step_kernel(const KArgs<Real> a) {
   constexpr int WPB = warps_per_block<Real, D>();
   extern __shared__ int4 smem_raw[];
   const int warp = threadIdx.x >> 5;

@@ -817,6 +817,58 @@ UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
   }
 }
 
+// ---------------------------------------------------------------- register-resident SPD solve (device only)
+// Same right-looking elimination as chol_solve_aug, but lane i keeps row i of the matrix in registers (lane N the right-hand
+// side) and the column entries travel by warp shuffle: step k costs one SHFL + one FFMA per remaining column for the whole
+// warp, with no shared-memory traffic and no loop / address arithmetic (~25 instructions per column instead of ~200).
+// Fully unrolled straight-line code (register indices must be static); it stays I-cache friendly because it is ONE
+// out-of-line copy used by every Newton iteration and by the Euler step, and a block's warps run it in lock-step.
+// Upper-triangle registers hold garbage that is never read by a valid lane.  Rows n..N-1 (model smaller than the size class)
+// are identity rows, so the padded system has the same solution.  The unit factor L overwrites `tri`, w = D^-1 L^-1 rhs
+// overwrites `rhs`; the back-substitution then runs with one unknown per lane (x_k broadcast by shuffle, L[k][lane] from
+// shared memory).  `x` may alias `rhs`.
+#ifndef UR3E_REG_CHOL
+#define UR3E_REG_CHOL 1
+#endif
+#if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
+template <typename Real, int N>
+__device__ __noinline__ void chol_solve_reg(Real* tri, Real* rhs, int n, Real* x) {
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = UR3E_LANE;
+  const bool isrow = lane < n, isrhs = lane == N;
+  Real* const row = isrow ? tri + lane * (lane + 1) / 2 : rhs;
+  const int jmax = isrow ? lane : (isrhs ? n - 1 : -1);   // this lane owns entries 0..jmax of `row`
+  Real a[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const Real ld = row[j <= jmax ? j : 0];
+    a[j] = j <= jmax ? ld : ((!isrow && j == lane) ? Real(1) : Real(0));
+  }
+  // A = L D L^T with unit L: after step k register a[k] of lane i > k holds L[i][k]; lane N ends with w
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    Real d = __shfl_sync(FULL, a[k], k);
+    d = d > Num<Real>::minval ? d : Num<Real>::minval;
+    const Real t = a[k] * (Real(1) / d);
+#pragma unroll
+    for (int j = k + 1; j < N; ++j) a[j] -= t * __shfl_sync(FULL, a[k], j);
+    a[k] = t;
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) if (j < jmax || (isrhs && j == jmax)) row[j] = a[j];   // strictly-lower L entries; all of w
+  __syncwarp();
+  Real xi = lane < n ? rhs[lane] : Real(0);
+#pragma unroll
+  for (int k = N - 1; k > 0; --k) {
+    const Real xk = __shfl_sync(FULL, xi, k);
+    if (lane < k && k < n) xi -= tri[k * (k + 1) / 2 + lane] * xk;
+  }
+  __syncwarp();
+  if (lane < n) x[lane] = xi;
+  __syncwarp();
+}
+#endif
+
 // ---------------------------------------------------------------- Newton solver on the primal problem
 // per-row cost derivative bookkeeping; cone contacts are processed by the lane that owns their normal row
 template <typename Real, typename D>
@@ -953,7 +1005,11 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
       }
       WARP_SYNC();
     }
+#if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
+    chol_solve_reg<Real, D::NV>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.search);
+#else
     chol_solve_aug(s, nv, s.search);
+#endif
     // Mv, jv, and the quadratic (Gauss) part of the line cost
     WARP_FOR(i, nv + nefc) {
       if (i < nv) s.Mv[i] = sym_matvec_row(s.M, s.search, i, nv);
@@ -998,7 +1054,11 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
     WARP_FOR(e, nv * (nv + 1) / 2 + nv) { s.fr.n.H[e] = e < nv * (nv + 1) / 2 ? s.M[e] : s.qfrc_smooth[e - nv * (nv + 1) / 2]; }
     WARP_FOR(d, nv) s.qfrc_constraint[d] = 0;
     WARP_SYNC();
+#if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
+    chol_solve_reg<Real, D::NV>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.qacc);
+#else
     chol_solve_aug(s, nv, s.qacc);
+#endif
     IF_LANE0 s.solver_iter = 0;
     // keep the block's barrier sequence: warps of the block that do have constraint rows iterate below
     if (aligned) { for (int it = 0; it < opt.max_iter; ++it) if (!BLOCK_ANY(false)) break; }
@@ -1114,11 +1174,18 @@ UR3E_PHASE void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
   Real* qa = s.qacc;
   if (m.has_damping) {
     // (M + h diag(damping)) a = qfrc_smooth + qfrc_constraint   
+#if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
+    // M is dead after this step (the next substep rebuilds it), so the damping goes onto its diagonal in place
+    WARP_FOR(d, nv) { s.M[d * (d + 1) / 2 + d] += h * m.dof_damping[d]; s.search[d] = s.qfrc_smooth[d] + s.qfrc_constraint[d]; }
+    WARP_SYNC();
+    chol_solve_reg<Real, D::NV>(s.M, s.search, nv, s.search);
+#else
     Real* A = s.fr.n.H;
     WARP_FOR(e, nv * (nv + 1) / 2) { const int ab = m.tri_ab[e]; A[e] = s.M[e] + ((ab >> 8) == (ab & 255) ? h * m.dof_damping[ab >> 8] : Real(0)); }
     WARP_FOR(d, nv) s.search[d] = s.qfrc_smooth[d] + s.qfrc_constraint[d];
     WARP_SYNC();
     tree_ldl_solve(m, s, s.search);
+#endif
     qa = s.search;
   }
   WARP_FOR(d, nv) s.st.qvel[d] += h * qa[d];
