@@ -988,8 +988,12 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
     for (int g = 0; g < s.ngrp; ++g) {
       const int r0 = s.grp_row0[g], r1 = r0 + s.grp_nrow[g], mask = s.grp_mask[g], kc = popcount32(mask);
       const bool contact = s.efc_type[r0] >= ROW_CON_N;
+      // column list of the group: cols[k] = index of the k-th set bit of its dof mask (solver scratch; __fns is a slow software loop)
+      uint8_t* cols = reinterpret_cast<uint8_t*>(s.colbuf[1]);
+      WARP_FOR(d, 32) if ((mask >> d) & 1) cols[popcount32(mask & (int)((1u << d) - 1u))] = (uint8_t)d;
+      WARP_SYNC();
       WARP_FOR(e, kc * (kc + 1) / 2) {
-        int pq = m.tri_ab[e], a = nth_set_bit(mask, pq >> 8), b = nth_set_bit(mask, pq & 255);
+        int pq = m.tri_ab[e], a = cols[pq >> 8], b = cols[pq & 255];
         Real h = 0;
         if (!contact) { for (int r = r0; r < r1; ++r) h += s.efc_Dact[r] * s.u.efc_J[r][a] * s.u.efc_J[r][b]; }
         else {
