@@ -29,6 +29,14 @@ DevModel<Real> compile_model(const HostModel& h) {
   const auto &par = h.I("body_parentid"), &bja = h.I("body_jntadr"), &bjn = h.I("body_jntnum"), &jt = h.I("jnt_type"), &jq = h.I("jnt_qposadr"), &jd = h.I("jnt_dofadr"),
              &root = h.I("body_rootid"), &dpar = h.I("dof_parentid"), &dbody = h.I("dof_bodyid"), &djnt = h.I("dof_jntid"), &jlim = h.I("jnt_limited");
   auto cp = [](Real* dst, const std::vector<double>& src, int off, int n) { for (int k = 0; k < n; ++k) dst[k] = (Real)src[off + k]; };
+  // unit quaternion (w, x, y, z) at src[off..off+4) -> row-major rotation matrix, evaluated in double
+  auto cpmat = [](Real* dst, const std::vector<double>& src, int off) {
+    double w = src[off], x = src[off + 1], y = src[off + 2], z = src[off + 3], n = std::sqrt(w * w + x * x + y * y + z * z);
+    if (n < 1e-15) { w = 1; x = y = z = 0; } else { w /= n; x /= n; y /= n; z /= n; }
+    const double R[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+                         2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z};
+    for (int k = 0; k < 9; ++k) dst[k] = (Real)R[k];
+  };
   std::vector<int> lastdof(h.nbody, -1);
   int nlevel = 1;
   for (int b = 0; b < h.nbody; ++b) {
@@ -36,8 +44,8 @@ DevModel<Real> compile_model(const HostModel& h) {
     m.body_level[b] = b == 0 ? 0 : m.body_level[par[b]] + 1;
     if (m.body_level[b] + 1 > nlevel) nlevel = m.body_level[b] + 1;
     m.body_root[b] = root[b];
-    cp(m.body_pos[b], h.D("body_pos"), 3 * b, 3); cp(m.body_quat[b], h.D("body_quat"), 4 * b, 4);
-    cp(m.body_ipos[b], h.D("body_ipos"), 3 * b, 3); cp(m.body_iquat[b], h.D("body_iquat"), 4 * b, 4);
+    cp(m.body_pos[b], h.D("body_pos"), 3 * b, 3); cpmat(m.body_mat[b], h.D("body_quat"), 4 * b);
+    cp(m.body_ipos[b], h.D("body_ipos"), 3 * b, 3); cpmat(m.body_imat[b], h.D("body_iquat"), 4 * b);
     m.body_mass[b] = (Real)h.D("body_mass")[b]; cp(m.body_inertia[b], h.D("body_inertia"), 3 * b, 3);
     cp(m.body_invw[b], h.D("body_invweight0"), 2 * b, 2);
     m.body_jkind[b] = JK_NONE; m.body_qadr[b] = -1; m.body_dadr[b] = -1;
@@ -50,7 +58,9 @@ DevModel<Real> compile_model(const HostModel& h) {
       req(jt[j] != JNT_FREE || par[b] == 0, "free joints must be children of the world");
       req(jt[j] != JNT_HINGE || root[b] != b, "a hinge body directly under the world needs a static base body above it");
       m.body_qadr[b] = jq[j]; m.body_dadr[b] = jd[j];
-      cp(m.jnt_pos[b], h.D("jnt_pos"), 3 * j, 3); cp(m.jnt_axis[b], h.D("jnt_axis"), 3 * j, 3);
+      cp(m.jnt_pos[b], h.D("jnt_pos"), 3 * j, 3);
+      { const double* ax = &h.D("jnt_axis")[3 * j]; double n = std::sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]); if (n < 1e-15) n = 1;
+        for (int k = 0; k < 3; ++k) m.jnt_axis[b][k] = (Real)(ax[k] / n); }   // unit axis (the kernel builds the joint rotation by Rodrigues' formula)
       m.jnt_q0[b] = (Real)h.D("qpos0")[jq[j]];
       int nd = jt[j] == JNT_FREE ? 6 : 1;
       for (int k = 0; k < nd; ++k) m.body_dofmask[b] |= 1u << (jd[j] + k);
@@ -59,6 +69,7 @@ DevModel<Real> compile_model(const HostModel& h) {
     m.body_lastdof[b] = lastdof[b];
   }
   m.nlevel = nlevel;
+  { int k = 0; for (int l = 1; l < nlevel; ++l) { m.lev_start[l] = k; for (int b = 1; b < h.nbody; ++b) if (m.body_level[b] == l) m.lev_body[k++] = b; } m.lev_start[nlevel] = k; m.lev_start[0] = 0; }
   int nfl = 0, damp = 0;
   for (int d = 0; d < h.nv; ++d) {
     int j = djnt[d];
@@ -119,7 +130,7 @@ DevModel<Real> compile_model(const HostModel& h) {
     req(ng < MAXG, "too many collidable geoms");
     int i = ng++; gmap[g] = i;
     m.geom_body[i] = gb[g]; m.geom_kind[i] = gt[g] == GEOM_PLANE ? GK_PLANE : GK_BOX;
-    cp(m.geom_pos[i], gpos, 3 * g, 3); cp(m.geom_quat[i], gquat, 4 * g, 4); cp(m.geom_size[i], gsize, 3 * g, 3);
+    cp(m.geom_pos[i], gpos, 3 * g, 3); cpmat(m.geom_mat[i], gquat, 4 * g); cp(m.geom_size[i], gsize, 3 * g, 3);
     m.geom_rbound[i] = gt[g] == GEOM_PLANE ? Real(0) : (Real)std::sqrt(gsize[3 * g] * gsize[3 * g] + gsize[3 * g + 1] * gsize[3 * g + 1] + gsize[3 * g + 2] * gsize[3 * g + 2]);
     return i;
   };
@@ -153,7 +164,7 @@ DevModel<Real> compile_model(const HostModel& h) {
   for (int k = 0; k < MAXSITE; ++k) {
     int sid = h.name2id(OBJ_SITE, tracked_site_names()[k]);
     if (sid < 0) break;   // tracked sites are a prefix: tcp, handle_site, right_pad1_site, left_pad1_site
-    m.site_body[ns] = h.I("site_bodyid")[sid]; cp(m.site_pos[ns], h.D("site_pos"), 3 * sid, 3); cp(m.site_quat[ns], h.D("site_quat"), 4 * sid, 4); ++ns;
+    m.site_body[ns] = h.I("site_bodyid")[sid]; cp(m.site_pos[ns], h.D("site_pos"), 3 * sid, 3); cpmat(m.site_mat[ns], h.D("site_quat"), 4 * sid); ++ns;
   }
   // main.xml has all four; ur3e_2f85.xml lacks handle_site: track tcp only there unless the prefix continues
   m.nsite = ns;

@@ -45,7 +45,9 @@ struct DevModel {
   // bodies (index 0 = world)
   int body_parent[MAXB], body_level[MAXB], body_jkind[MAXB], body_qadr[MAXB], body_dadr[MAXB], body_lastdof[MAXB], body_root[MAXB];
   uint32_t body_dofmask[MAXB];  // bit d set when dof d moves the body
-  Real body_pos[MAXB][3], body_quat[MAXB][4], body_ipos[MAXB][3], body_iquat[MAXB][4], body_mass[MAXB], body_inertia[MAXB][3];
+  int lev_start[MAXB + 1], lev_body[MAXB];   // bodies grouped by tree depth: level l (>= 1) = lev_body[lev_start[l] .. lev_start[l+1])
+  // constant rotations are stored as row-major 3x3 matrices (body frame in the parent, inertial frame in the body)
+  Real body_pos[MAXB][3], body_mat[MAXB][9], body_ipos[MAXB][3], body_imat[MAXB][9], body_mass[MAXB], body_inertia[MAXB][3];
   Real body_invw[MAXB][2];
   Real jnt_pos[MAXB][3], jnt_axis[MAXB][3], jnt_q0[MAXB];  // the (single) joint of each body
   // dofs
@@ -60,7 +62,7 @@ struct DevModel {
   int tri_ab[(MAXV + 1) * (MAXV + 2) / 2];  // (a << 8 | b), b <= a, row-major lower triangle of the (nv+1)^2 augmented matrix
   // collidable geoms
   int geom_body[MAXG], geom_kind[MAXG];
-  Real geom_pos[MAXG][3], geom_quat[MAXG][4], geom_size[MAXG][3], geom_rbound[MAXG];
+  Real geom_pos[MAXG][3], geom_mat[MAXG][9], geom_size[MAXG][3], geom_rbound[MAXG];
   // candidate pairs (geom1 = plane for plane-box)
   int pair_g1[MAXPAIR], pair_g2[MAXPAIR], pair_src_g1[MAXPAIR], pair_src_g2[MAXPAIR];
   Real pair_friction[MAXPAIR][2], pair_solref[MAXPAIR][2], pair_solimp[MAXPAIR][5], pair_margin[MAXPAIR], pair_includemargin[MAXPAIR], pair_invw[MAXPAIR];
@@ -69,7 +71,7 @@ struct DevModel {
   Real eq_data[MAXEQ][6], eq_solref[MAXEQ][2], eq_solimp[MAXEQ][5], eq_invw[MAXEQ];
   // tracked sites
   int site_body[MAXSITE];
-  Real site_pos[MAXSITE][3], site_quat[MAXSITE][4];
+  Real site_pos[MAXSITE][3], site_mat[MAXSITE][9];
   // actuators: force = gain*ctrl + b0 + b1*len + b2*vel ; moment over at most two dofs
   int act_dof[MAXU][2], act_ctrllimited[MAXU], act_forcelimited[MAXU];
   Real act_coef[MAXU][2], act_gain[MAXU], act_bias[MAXU][3], act_ctrlrange[MAXU][2], act_forcerange[MAXU][2];

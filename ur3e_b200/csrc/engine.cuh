@@ -52,7 +52,7 @@ struct Arena {
   Real qacc[D::NV], ctrl[D::NU], act_force[D::NU];
   Real xpos[D::NB][3];
   union {   // body frames are dead once the constraint rows exist; the Newton / Euler matrix reuses their storage
-    struct { Real xquat[D::NB][4], xmat[D::NB][9], xipos[D::NB][3]; } k;
+    struct { Real xmat[D::NB][9], xipos[D::NB][3]; } k;
     struct { Real H[(D::NV + 1) * (D::NV + 2) / 2]; } n;   // augmented Newton / Euler matrix, packed lower triangle: (i,j) at i(i+1)/2 + j
   } fr;
   union { alignas(16) Real colbuf[2][32]; Real obs[32]; };   // solver scratch / the step's observation (written after the last solve)
@@ -78,6 +78,7 @@ struct Arena {
   int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
   union {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
+    struct { Real lmat[D::NB][9], lpos[D::NB][3]; } kin;   // kinematics only: each body's frame relative to its parent
     Real stage[D::NPAIR][STAGE_W];   // per candidate pair: shared normal (3), then up to STAGE_PTS x (pos 3, dist 1)
     Real efc_J[D::MAXDENSE][D::NV];   // dense rows only
   } u;
@@ -183,82 +184,101 @@ template <typename Real> UR3E_HD Real sym_matvec_row(const Real* A, const Real* 
 }
 
 // ---------------------------------------------------------------- kinematics
-template <typename Real, typename D>
-UR3E_HD void fk_body(const DevModel<Real>& m, Arena<Real, D>& s, int b) {
-  int p = m.body_parent[b], jk = m.body_jkind[b];
-  Real pos[3], quat[4];
-  if (jk == JK_FREE) {
-    int qa = m.body_qadr[b], da = m.body_dadr[b];
-    for (int k = 0; k < 3; ++k) pos[k] = s.st.qpos[qa + k];
-    for (int k = 0; k < 4; ++k) quat[k] = s.st.qpos[qa + 3 + k];
-    quat_normalize(quat);
-    Real R[9]; quat2mat(R, quat);
-    for (int i = 0; i < 3; ++i) {
-      Real* ct = s.cdof[da + i]; Real* cr = s.cdof[da + 3 + i];
-      for (int k = 0; k < 6; ++k) { ct[k] = 0; cr[k] = 0; }
-      ct[3 + i] = 1;                                            // translation along world axis i
-      cr[0] = R[i]; cr[1] = R[3 + i]; cr[2] = R[6 + i];         // rotation about body axis i, through the reference point
-    }
-  } else {
-    Real v[3];
-    mat_vec3(v, s.fr.k.xmat[p], m.body_pos[b]);
-    for (int k = 0; k < 3; ++k) pos[k] = s.xpos[p][k] + v[k];
-    quat_mul(quat, s.fr.k.xquat[p], m.body_quat[b]);
-    if (jk == JK_HINGE) {
-      Real R0[9], anchor[3], axis[3], vec[3];
-      quat2mat(R0, quat);
-      mat_vec3(vec, R0, m.jnt_pos[b]);
-      for (int k = 0; k < 3; ++k) anchor[k] = pos[k] + vec[k];
-      mat_vec3(axis, R0, m.jnt_axis[b]);
-      Real ang = s.st.qpos[m.body_qadr[b]] - m.jnt_q0[b], sn, cs;
-      Num<Real>::sincos(ang * Real(0.5), &sn, &cs);
-      Real ql[4] = {cs, m.jnt_axis[b][0] * sn, m.jnt_axis[b][1] * sn, m.jnt_axis[b][2] * sn};
-      quat_mul(quat, quat, ql);
-      quat_normalize(quat);
-      Real R1[9]; quat2mat(R1, quat);
-      mat_vec3(vec, R1, m.jnt_pos[b]);
-      for (int k = 0; k < 3; ++k) pos[k] = anchor[k] - vec[k];
-      const Real* ref = s.xpos[m.body_root[b]];
-      Real off[3] = {ref[0] - anchor[0], ref[1] - anchor[1], ref[2] - anchor[2]};
-      Real* c = s.cdof[m.body_dadr[b]];
-      c[0] = axis[0]; c[1] = axis[1]; c[2] = axis[2];
-      cross3(c + 3, axis, off);
-    } else {
-      quat_normalize(quat);
-    }
-  }
-  for (int k = 0; k < 3; ++k) s.xpos[b][k] = pos[k];
-  for (int k = 0; k < 4; ++k) s.fr.k.xquat[b][k] = quat[k];
-  quat2mat(s.fr.k.xmat[b], quat);
-  Real v[3];
-  mat_vec3(v, s.fr.k.xmat[b], m.body_ipos[b]);
-  for (int k = 0; k < 3; ++k) s.fr.k.xipos[b][k] = pos[k] + v[k];
+// r = a b for row-major 3x3 matrices (r must not alias a or b)
+template <typename Real> UR3E_HD void mat_mul3(Real* r, const Real* a, const Real* b) {
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
 }
 
+// Frames are composed as rotation matrices in three stages, so that the serial part (one step per tree level) is only a
+// 3x3 product spread over 12 lanes per body:
+//   A. every body in parallel: its frame relative to the parent, (L_b, t_b) = body offset * joint transform
+//   B. level by level: R_b = R_p L_b, x_b = x_p + R_p t_b   (lane = one entry of R_b or x_b)
+//   C. every body / geom / site in parallel: inertial frame position, joint axis (cdof), geom and site frames
 template <typename Real, typename D>
 UR3E_PHASE void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
-  IF_LANE0 {
-    for (int k = 0; k < 3; ++k) { s.xpos[0][k] = 0; s.fr.k.xipos[0][k] = 0; }
-    s.fr.k.xquat[0][0] = 1; s.fr.k.xquat[0][1] = s.fr.k.xquat[0][2] = s.fr.k.xquat[0][3] = 0;
-    for (int k = 0; k < 9; ++k) s.fr.k.xmat[0][k] = (k % 4 == 0) ? Real(1) : Real(0);
+  auto& kin = s.u.kin;
+  WARP_FOR(b, m.nbody) {
+    Real* L = kin.lmat[b]; Real* t = kin.lpos[b];
+    const int jk = m.body_jkind[b];
+    if (b == 0) {
+      for (int k = 0; k < 9; ++k) s.fr.k.xmat[0][k] = (k % 4 == 0) ? Real(1) : Real(0);
+      for (int k = 0; k < 3; ++k) { s.xpos[0][k] = 0; s.fr.k.xipos[0][k] = 0; }
+    } else if (jk == JK_FREE) {
+      const int qa = m.body_qadr[b];
+      Real q[4] = {s.st.qpos[qa + 3], s.st.qpos[qa + 4], s.st.qpos[qa + 5], s.st.qpos[qa + 6]};
+      quat_normalize(q); quat2mat(L, q);
+      for (int k = 0; k < 3; ++k) t[k] = s.st.qpos[qa + k];
+    } else if (jk == JK_HINGE) {
+      // joint rotation about the (unit) axis a by Rodrigues' formula; the joint anchor stays fixed in the parent frame
+      const Real* a = m.jnt_axis[b]; const Real* jp = m.jnt_pos[b]; const Real* Rb = m.body_mat[b];
+      Real sn, cs; Num<Real>::sincos(s.st.qpos[m.body_qadr[b]] - m.jnt_q0[b], &sn, &cs);
+      const Real v = 1 - cs;
+      const Real Rj[9] = {cs + v * a[0] * a[0], v * a[0] * a[1] - sn * a[2], v * a[0] * a[2] + sn * a[1],
+                          v * a[0] * a[1] + sn * a[2], cs + v * a[1] * a[1], v * a[1] * a[2] - sn * a[0],
+                          v * a[0] * a[2] - sn * a[1], v * a[1] * a[2] + sn * a[0], cs + v * a[2] * a[2]};
+      mat_mul3(L, Rb, Rj);
+      Real rj[3], d[3]; mat_vec3(rj, Rj, jp);
+      for (int k = 0; k < 3; ++k) rj[k] = jp[k] - rj[k];
+      mat_vec3(d, Rb, rj);
+      for (int k = 0; k < 3; ++k) t[k] = m.body_pos[b][k] + d[k];
+    } else {
+      for (int k = 0; k < 9; ++k) L[k] = m.body_mat[b][k];
+      for (int k = 0; k < 3; ++k) t[k] = m.body_pos[b][k];
+    }
   }
   WARP_SYNC();
   for (int lev = 1; lev < m.nlevel; ++lev) {
-    WARP_FOR(b, m.nbody) if (m.body_level[b] == lev) fk_body(m, s, b);
+    const int b0 = m.lev_start[lev], cnt = m.lev_start[lev + 1] - b0;
+    WARP_FOR(i, 12 * cnt) {
+      const int slot = i / 12, e = i - 12 * slot, b = m.lev_body[b0 + slot], p = m.body_parent[b];
+      if (e < 9) {
+        const int r = e / 3, c = e - 3 * r;
+        const Real* Rp = s.fr.k.xmat[p] + 3 * r; const Real* L = kin.lmat[b] + c;
+        s.fr.k.xmat[b][e] = Rp[0] * L[0] + Rp[1] * L[3] + Rp[2] * L[6];
+      } else {
+        const int r = e - 9;
+        const Real* Rp = s.fr.k.xmat[p] + 3 * r; const Real* t = kin.lpos[b];
+        s.xpos[b][r] = s.xpos[p][r] + Rp[0] * t[0] + Rp[1] * t[1] + Rp[2] * t[2];
+      }
+    }
     WARP_SYNC();
   }
-  // geoms and tracked sites
-  WARP_FOR(i, m.ngeom + m.nsite) {
-    if (i < m.ngeom) {
-      int b = m.geom_body[i]; Real v[3], q[4];
-      mat_vec3(v, s.fr.k.xmat[b], m.geom_pos[i]);
-      for (int k = 0; k < 3; ++k) s.geom_xpos[i][k] = s.xpos[b][k] + v[k];
-      quat_mul(q, s.fr.k.xquat[b], m.geom_quat[i]); quat2mat(s.geom_xmat[i], q);
+  WARP_FOR(i, m.nbody + m.ngeom + m.nsite) {
+    if (i < m.nbody) {
+      const int b = i;
+      if (b > 0) {
+        const Real* R = s.fr.k.xmat[b]; const Real* x = s.xpos[b];
+        Real v[3]; mat_vec3(v, R, m.body_ipos[b]);
+        for (int k = 0; k < 3; ++k) s.fr.k.xipos[b][k] = x[k] + v[k];
+        const int jk = m.body_jkind[b];
+        if (jk == JK_HINGE) {
+          Real axis[3], anchor[3];
+          mat_vec3(axis, R, m.jnt_axis[b]); mat_vec3(anchor, R, m.jnt_pos[b]);
+          const Real* ref = s.xpos[m.body_root[b]];
+          const Real off[3] = {ref[0] - x[0] - anchor[0], ref[1] - x[1] - anchor[1], ref[2] - x[2] - anchor[2]};
+          Real* c = s.cdof[m.body_dadr[b]];
+          c[0] = axis[0]; c[1] = axis[1]; c[2] = axis[2];
+          cross3(c + 3, axis, off);
+        } else if (jk == JK_FREE) {
+          const int da = m.body_dadr[b];
+          for (int a = 0; a < 3; ++a) {
+            Real* ct = s.cdof[da + a]; Real* cr = s.cdof[da + 3 + a];
+            for (int k = 0; k < 6; ++k) { ct[k] = 0; cr[k] = 0; }
+            ct[3 + a] = 1;                                            // translation along world axis a
+            cr[0] = R[a]; cr[1] = R[3 + a]; cr[2] = R[6 + a];         // rotation about body axis a, through the reference point
+          }
+        }
+      }
+    } else if (i < m.nbody + m.ngeom) {
+      const int g = i - m.nbody, b = m.geom_body[g]; Real v[3];
+      mat_vec3(v, s.fr.k.xmat[b], m.geom_pos[g]);
+      for (int k = 0; k < 3; ++k) s.geom_xpos[g][k] = s.xpos[b][k] + v[k];
+      mat_mul3(s.geom_xmat[g], s.fr.k.xmat[b], m.geom_mat[g]);
     } else {
-      int j = i - m.ngeom, b = m.site_body[j]; Real v[3], q[4];
+      const int j = i - m.nbody - m.ngeom, b = m.site_body[j]; Real v[3];
       mat_vec3(v, s.fr.k.xmat[b], m.site_pos[j]);
       for (int k = 0; k < 3; ++k) s.site_xpos[j][k] = s.xpos[b][k] + v[k];
-      if (j == 0) { quat_mul(q, s.fr.k.xquat[b], m.site_quat[j]); quat2mat(s.site_xmat[0], q); }
+      if (j == 0) mat_mul3(s.site_xmat[0], s.fr.k.xmat[b], m.site_mat[0]);
     }
   }
   WARP_SYNC();
@@ -276,7 +296,7 @@ UR3E_PHASE void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
     else {
       const Real* ref = s.xpos[m.body_root[b]];
       Real dif[3] = {s.fr.k.xipos[b][0] - ref[0], s.fr.k.xipos[b][1] - ref[1], s.fr.k.xipos[b][2] - ref[2]};
-      Real q[4], R[9]; quat_mul(q, s.fr.k.xquat[b], m.body_iquat[b]); quat2mat(R, q);
+      Real R[9]; mat_mul3(R, s.fr.k.xmat[b], m.body_imat[b]);
       const Real* in = m.body_inertia[b]; Real mass = m.body_mass[b];
       Real t00 = 0, t11 = 0, t22 = 0, t01 = 0, t02 = 0, t12 = 0;
       for (int k = 0; k < 3; ++k) {
