@@ -842,7 +842,7 @@ UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
 // side) and the column entries travel by warp shuffle: step k costs one SHFL + one FFMA per remaining column for the whole
 // warp, with no shared-memory traffic and no loop / address arithmetic (~25 instructions per column instead of ~200).
 // Fully unrolled straight-line code (register indices must be static); it stays I-cache friendly because it is ONE
-// out-of-line copy used by every Newton iteration and by the Euler step, and a block's warps run it in lock-step.
+// out-of-line copy used by every Newton iteration and by the Euler step, and the warps of a block reach it at about the same time.
 // Upper-triangle registers hold garbage that is never read by a valid lane.  Rows n..N-1 (model smaller than the size class)
 // are identity rows, so the padded system has the same solution.  The unit factor L overwrites `tri`, w = D^-1 L^-1 rhs
 // overwrites `rhs`; the back-substitution then runs with one unknown per lane (x_k broadcast by shuffle, L[k][lane] from
@@ -1071,7 +1071,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
 }
 
 template <typename Real, typename D>
-UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, bool aligned = false) {
+UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
   const int nv = m.nv, nefc = s.nefc;
   if (nefc == 0) {
     // unconstrained: qacc = M^-1 qfrc_smooth
@@ -1084,8 +1084,6 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
     chol_solve_aug(s, nv, s.qacc);
 #endif
     IF_LANE0 s.solver_iter = 0;
-    // keep the block's barrier sequence: warps of the block that do have constraint rows iterate below
-    if (aligned) { for (int it = 0; it < opt.max_iter; ++it) if (!BLOCK_ANY(false)) break; }
     return;
   }
   const Real scale = Real(1) / (m.meaninertia * Real(nv > 1 ? nv : 1));
@@ -1096,17 +1094,13 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
     else { int r = i - nv; s.efc_jar[r] = row_dot(m, s, r, s.qacc) - s.efc_aref[r]; }
   }
   WARP_SYNC();
-  // Newton iterations.  In the aligned (regular substep) case the block's warps iterate in lock-step: a converged warp
-  // idles at the barrier while the others iterate, which keeps every warp of the block inside the same few KB of code.
+  // Newton iterations; each warp runs its own count (the block re-aligns at the barrier that follows the solve: lock-stepping
+  // the iterations themselves measured 1.5 % slower once the iteration became cheap, profiles/r1_summary.md)
   int iter = 0;
-  bool done = false;
   for (int it = 0; it < opt.max_iter; ++it) {
-    if (aligned) { if (!BLOCK_ANY(!done)) break; } else if (done) break;
-    if (!done) {
-      const int rc = newton_iteration(m, s, opt, scale);
-      if (rc != 1) ++iter;
-      done = rc != 0;
-    }
+    const int rc = newton_iteration(m, s, opt, scale);
+    if (rc != 1) ++iter;
+    if (rc != 0) break;
   }
   constraint_update(m, s, false);
   WARP_FOR(d, nv) s.qfrc_constraint[d] = col_dot(m, s, d, s.efc_force);
@@ -1116,7 +1110,7 @@ UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOp
 
 // ---------------------------------------------------------------- one mj_step
 template <typename Real, typename D>
-UR3E_PHASE void forward(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, bool with_solver, bool aligned = false) {
+UR3E_HD void forward(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, bool with_solver, bool aligned = false) {
   // `aligned`: every warp of the block is on this path (the regular substep), so block-wide barriers keep the warps in the
   // same phase and they share its code in the SM's instruction cache; all other callers (reset, set_state, redo after a
   // bad qacc) are warp-divergent and must not touch the barrier.
@@ -1129,7 +1123,7 @@ UR3E_PHASE void forward(const DevModel<Real>& m, Arena<Real, D>& s, const Solver
     if (aligned) BLOCK_SYNC();
     make_constraint(m, s);
     if (aligned) BLOCK_SYNC();
-    solve(m, s, opt, aligned);
+    solve(m, s, opt);
   }
 }
 
@@ -1232,7 +1226,7 @@ UR3E_PHASE void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
 
 // returns a warning mask: 1 bad qpos, 2 bad qvel, 4 bad qacc (mj_checkPos/Vel/Acc + autoreset)
 template <typename Real, typename D>
-UR3E_PHASE int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
+UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
   int w = 0;
   WARP_FOR(i, m.nq + m.nv) w |= i < m.nq ? is_bad(s.st.qpos[i]) : 2 * is_bad(s.st.qvel[i - m.nq]);
   w = warp_or(w);

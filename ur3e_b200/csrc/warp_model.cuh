@@ -28,7 +28,6 @@
 #define WARP_FOR(i, n) for (int i = UR3E_LANE; i < (n); i += 32)
 #define WARP_SYNC() __syncwarp()
 #define BLOCK_SYNC() __syncthreads()
-#define BLOCK_ANY(pred) (__syncthreads_or((int)(pred)) != 0)
 #define IF_LANE0 if (UR3E_LANE == 0)
 #define UR3E_LDG(x) __ldg(&(x))
 // per-lane private array (registers); the host build keeps one copy per emulated lane
@@ -55,7 +54,6 @@ __device__ __forceinline__ int nth_set_bit(int v, int n) { return (int)__fns((un
 #define WARP_FOR(i, n) for (int i = 0; i < (n); ++i)
 #define WARP_SYNC() ((void)0)
 #define BLOCK_SYNC() ((void)0)
-#define BLOCK_ANY(pred) (pred)
 #define IF_LANE0
 #define UR3E_LDG(x) (x)
 #define LANE_ARRAY(T, name, N) T name[32][N]
