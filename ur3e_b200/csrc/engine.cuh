@@ -76,6 +76,7 @@ struct Arena {
   uint8_t sp_fl[D::NV], sp_lo[D::NV], sp_hi[D::NV], sp_ej[D::NV];
   int nd, rf0, rl0;   // dense rows [0, nd); friction rows from rf0, limit rows from rl0
   int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
+  int sum_ncon, sum_nefc, sum_iter, warn;   // accumulated over the substeps of one env step
   union {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
     struct { Real lmat[D::NB][9], lpos[D::NB][3]; } kin;   // kinematics only: each body's frame relative to its parent

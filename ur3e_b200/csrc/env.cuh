@@ -288,18 +288,22 @@ UR3E_PHASE void env_reset(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<
 
 // ---------------------------------------------------------------- one environment step
 template <typename Real, typename D>
-UR3E_PHASE StepOut<Real> env_step(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const SolverOpts<Real>& opt, const Real* act) {
+UR3E_HD StepOut<Real> env_step(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const SolverOpts<Real>& opt, const Real* act) {
   IF_LANE0 { s.overflow = 0; }
   controller(m, c, s, act);
-  int warn = 0;
-  float sn = 0, sc = 0, si = 0;
-  int mxc = 0, mxe = 0;
+  // per-step counters live in the arena, not in registers: nothing but the loop counter stays live across the substep calls
+  IF_LANE0 { s.max_ncon = 0; s.max_nefc = 0; s.sum_ncon = 0; s.sum_nefc = 0; s.sum_iter = 0; s.warn = 0; }
   for (int k = 0; k < c.frame_skip; ++k) {
-    warn |= substep(m, s, opt);
-    sn += (float)s.nefc; sc += (float)s.ncon; si += (float)s.solver_iter;
-    mxc = s.ncon > mxc ? s.ncon : mxc; mxe = s.nefc > mxe ? s.nefc : mxe;
+    const int w = substep(m, s, opt);
+    IF_LANE0 {
+      s.warn |= w; s.sum_nefc += s.nefc; s.sum_ncon += s.ncon; s.sum_iter += s.solver_iter;
+      if (s.ncon > s.max_ncon) s.max_ncon = s.ncon;
+      if (s.nefc > s.max_nefc) s.max_nefc = s.nefc;
+    }
   }
-  IF_LANE0 { s.max_ncon = mxc; s.max_nefc = mxe; }
+  WARP_SYNC();
+  const int warn = s.warn;
+  const float sn = (float)s.sum_nefc, sc = (float)s.sum_ncon, si = (float)s.sum_iter;
   update_cache(m, c, s);
   ContactFlags cf = contact_flags(m, c, s);
   write_obs(m, c, s, cf);
