@@ -1072,7 +1072,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
 }
 
 template <typename Real, typename D>
-UR3E_PHASE void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
+UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
   const int nv = m.nv, nefc = s.nefc;
   if (nefc == 0) {
     // unconstrained: qacc = M^-1 qfrc_smooth
@@ -1127,6 +1127,10 @@ UR3E_HD void forward(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpt
     solve(m, s, opt);
   }
 }
+
+// out-of-line copy of the full forward pass for the rare paths (redo after a bad qacc, reset): keeps them out of the step's hot code
+template <typename Real, typename D>
+UR3E_PHASE void forward_cold(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) { forward(m, s, opt, true); }
 
 template <typename Real, typename D>
 UR3E_PHASE void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
@@ -1236,7 +1240,7 @@ UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts
   int wa = 0;
   WARP_FOR(i, m.nv) wa |= 4 * is_bad(s.qacc[i]);
   wa = warp_or(wa);
-  if (wa) { reset_data(m, s); forward(m, s, opt, true); w |= wa; }
+  if (wa) { reset_data(m, s); forward_cold(m, s, opt); w |= wa; }
   WARP_FOR(d, m.nv) s.st.qacc_ws[d] = s.qacc[d];
   BLOCK_SYNC();
   euler(m, s);
