@@ -516,7 +516,7 @@ UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Rea
 }
 
 template <typename Real, typename D>
-UR3E_PHASE void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
   if constexpr (!D::HAS_CONTACT) { s.ncon = 0; return; }
   else {
     WARP_FOR(p, m.npair) {
@@ -1192,7 +1192,7 @@ UR3E_PHASE void tree_ldl_solve(const DevModel<Real>& m, Arena<Real, D>& s, Real*
 }
 
 template <typename Real, typename D>
-UR3E_PHASE void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nv = m.nv; const Real h = m.timestep;
   Real* qa = s.qacc;
   if (m.has_damping) {
