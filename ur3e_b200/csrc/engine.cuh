@@ -873,10 +873,8 @@ __device__ __noinline__ void chol_solve_reg(Real* tri, Real* rhs, int n, Real* x
     const Real t = a[k] * (Real(1) / d);
 #pragma unroll
     for (int j = k + 1; j < N; ++j) a[j] -= t * __shfl_sync(FULL, a[k], j);
-    a[k] = t;
+    if (k < jmax || (isrhs && k == jmax)) row[k] = t;   // strictly-lower L entries, all of w; stored at once, which frees the register
   }
-#pragma unroll
-  for (int j = 0; j < N; ++j) if (j < jmax || (isrhs && j == jmax)) row[j] = a[j];   // strictly-lower L entries; all of w
   __syncwarp();
   Real xi = lane < n ? rhs[lane] : Real(0);
 #pragma unroll
