@@ -15,6 +15,9 @@
 #ifndef UR3E_BLOCKS_PER_SM
 #define UR3E_BLOCKS_PER_SM 2
 #endif
+#ifndef UR3E_MAX_WPB
+#define UR3E_MAX_WPB 16
+#endif
 
 namespace ur3e {
 enum Op { OP_STEP = 0, OP_RESET = 1, OP_SET_STATE = 2, OP_DEBUG = 3 };
@@ -46,7 +49,7 @@ template <typename Real, typename D> __host__ __device__ constexpr int warps_per
   // UR3E_BLOCKS_PER_SM co-resident blocks: while one block waits at a barrier the other keeps the issue slots busy
   int per_sm = (int)((233472 - 1024 * UR3E_BLOCKS_PER_SM) / arena_stride<Real, D>());
   int w = per_sm / UR3E_BLOCKS_PER_SM;
-  return w > 16 ? 16 : (w < 1 ? 1 : w);
+  return w > UR3E_MAX_WPB ? UR3E_MAX_WPB : (w < 1 ? 1 : w);
 }
 constexpr int DBG_DOUBLES = MAXV * MAXV + 3 * MAXV + 8 + 4 * MAXCON + CACHE_SIZE;
 

@@ -1113,15 +1113,18 @@ UR3E_HD void forward(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpt
   // `aligned`: every warp of the block is on this path (the regular substep), so block-wide barriers keep the warps in the
   // same phase and they share its code in the SM's instruction cache; all other callers (reset, set_state, redo after a
   // bad qacc) are warp-divergent and must not touch the barrier.
+#ifndef UR3E_BARRIERS
+#define UR3E_BARRIERS 31   // bit i: barrier i of the substep is on (A/B knob; kinematics|dynamics|collision|rows|solve|euler)
+#endif
   kinematics(m, s);
-  if (aligned) BLOCK_SYNC();
+  if (aligned && (UR3E_BARRIERS & 1)) BLOCK_SYNC();
   dynamics(m, s);
-  if (aligned) BLOCK_SYNC();
+  if (aligned && (UR3E_BARRIERS & 2)) BLOCK_SYNC();
   collision(m, s);
   if (with_solver) {
-    if (aligned) BLOCK_SYNC();
+    if (aligned && (UR3E_BARRIERS & 4)) BLOCK_SYNC();
     make_constraint(m, s);
-    if (aligned) BLOCK_SYNC();
+    if (aligned && (UR3E_BARRIERS & 8)) BLOCK_SYNC();
     solve(m, s, opt);
   }
 }
@@ -1240,7 +1243,7 @@ UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts
   wa = warp_or(wa);
   if (wa) { reset_data(m, s); forward_cold(m, s, opt); w |= wa; }
   WARP_FOR(d, m.nv) s.st.qacc_ws[d] = s.qacc[d];
-  BLOCK_SYNC();
+  if (UR3E_BARRIERS & 16) BLOCK_SYNC(); else WARP_SYNC();
   euler(m, s);
   return w;
 }
