@@ -81,12 +81,12 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
     WARP_FOR(i, m.nq) s.st.qpos[i] = a.qpos_in[e * m.nq + i];
     WARP_FOR(i, m.nv) { s.st.qvel[i] = a.qvel_in[e * m.nv + i]; s.st.qacc_ws[i] = a.ws_in ? a.ws_in[e * m.nv + i] : Real(0); }
     WARP_SYNC();
-    forward(m, s, a.opt, false);
+    forward_cold(m, s, a.opt, false);
     update_cache(m, c, s);
   } else {  // OP_DEBUG: full forward at the current state, dump internals of one environment
     WARP_FOR(i, m.nu) s.ctrl[i] = 0;
     WARP_SYNC();
-    forward(m, s, a.opt, true);
+    forward_cold(m, s, a.opt, true);
     update_cache(m, c, s);
     double* o = a.dbg;
     const int nv = m.nv;

@@ -196,7 +196,7 @@ template <typename Real> UR3E_HD void mat_mul3(Real* r, const Real* a, const Rea
 //   B. level by level: R_b = R_p L_b, x_b = x_p + R_p t_b   (lane = one entry of R_b or x_b)
 //   C. every body / geom / site in parallel: inertial frame position, joint axis (cdof), geom and site frames
 template <typename Real, typename D>
-UR3E_PHASE void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
   auto& kin = s.u.kin;
   WARP_FOR(b, m.nbody) {
     Real* L = kin.lmat[b]; Real* t = kin.lpos[b];
@@ -287,7 +287,7 @@ UR3E_PHASE void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
 
 // ---------------------------------------------------------------- CRBA + RNE
 template <typename Real, typename D>
-UR3E_PHASE void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nb = m.nbody, nv = m.nv;
   auto& y = s.u.dyn;
   // body inertias about the tree reference point + body velocities (sum over the dof chain)
@@ -614,7 +614,7 @@ UR3E_HD Real col_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int d, co
 }
 
 template <typename Real, typename D>
-UR3E_PHASE void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nv = m.nv;
   // row budget: dense rows = connect equalities + contacts (3 rows each), sparse rows = joint equalities, friction loss, limits
   int ndeq = 0, nej = 0;
@@ -1131,7 +1131,7 @@ UR3E_HD void forward(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpt
 
 // out-of-line copy of the full forward pass for the rare paths (redo after a bad qacc, reset): keeps them out of the step's hot code
 template <typename Real, typename D>
-UR3E_PHASE void forward_cold(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) { forward(m, s, opt, true); }
+UR3E_PHASE void forward_cold(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, bool with_solver) { forward(m, s, opt, with_solver); }
 
 template <typename Real, typename D>
 UR3E_PHASE void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
@@ -1241,7 +1241,7 @@ UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts
   int wa = 0;
   WARP_FOR(i, m.nv) wa |= 4 * is_bad(s.qacc[i]);
   wa = warp_or(wa);
-  if (wa) { reset_data(m, s); forward_cold(m, s, opt); w |= wa; }
+  if (wa) { reset_data(m, s); forward_cold(m, s, opt, true); w |= wa; }
   WARP_FOR(d, m.nv) s.st.qacc_ws[d] = s.qacc[d];
   if (UR3E_BARRIERS & 16) BLOCK_SYNC(); else WARP_SYNC();
   euler(m, s);

@@ -282,7 +282,7 @@ UR3E_PHASE void env_reset(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<
   }
   IF_LANE0 { s.st.t = 0; s.st.ep_return = 0; s.st.episode += 1; }
   WARP_SYNC();
-  forward(m, s, opt, false);   // set_state -> mj_forward: fresh kinematics, bias and contacts; warm start stays zero
+  forward_cold(m, s, opt, false);   // set_state -> mj_forward: fresh kinematics, bias and contacts; warm start stays zero
   update_cache(m, c, s);
 }
 
