@@ -891,7 +891,7 @@ __device__ __noinline__ void chol_solve_reg(Real* tri, Real* rhs, int n, Real* x
 // ---------------------------------------------------------------- Newton solver on the primal problem
 // per-row cost derivative bookkeeping; cone contacts are processed by the lane that owns their normal row
 template <typename Real, typename D>
-UR3E_PHASE void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bool want_hess) {
+UR3E_HD void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bool want_hess) {
   WARP_FOR(r, s.nefc) {
     int t = s.efc_type[r];
     Real Dr = s.efc_D[r], x = s.efc_jar[r];
@@ -934,7 +934,7 @@ UR3E_PHASE void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bo
 
 // derivative / curvature of the cost along qacc + alpha * search (constraint part)
 template <typename Real, typename D>
-UR3E_PHASE void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real alpha, Real g1, Real g2, Real* dphi, Real* ddphi) {
+UR3E_HD void line_eval(const DevModel<Real>& m, const Arena<Real, D>& s, Real alpha, Real g1, Real g2, Real* dphi, Real* ddphi) {
   Real p1 = 0, p2 = 0;
   WARP_FOR(r, s.nefc) {
     int t = s.efc_type[r];
