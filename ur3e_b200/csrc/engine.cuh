@@ -853,7 +853,7 @@ UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
 #endif
 #if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
 template <typename Real, int N>
-__device__ __noinline__ void chol_solve_reg(Real* tri, Real* rhs, int n, Real* x) {
+__device__ __forceinline__ void chol_solve_reg_body(Real* tri, Real* rhs, int n, Real* x) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = UR3E_LANE;
   const bool isrow = lane < n, isrhs = lane == N;
@@ -886,6 +886,8 @@ __device__ __noinline__ void chol_solve_reg(Real* tri, Real* rhs, int n, Real* x
   if (lane < n) x[lane] = xi;
   __syncwarp();
 }
+template <typename Real, int N>
+__device__ __noinline__ void chol_solve_reg(Real* tri, Real* rhs, int n, Real* x) { chol_solve_reg_body<Real, N>(tri, rhs, n, x); }
 #endif
 
 // ---------------------------------------------------------------- Newton solver on the primal problem
@@ -1029,7 +1031,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
       WARP_SYNC();
     }
 #if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
-    chol_solve_reg<Real, D::NV>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.search);
+    chol_solve_reg_body<Real, D::NV>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.search);   // inlined in the Newton loop; the Euler step and the unconstrained case share the out-of-line copy
 #else
     chol_solve_aug(s, nv, s.search);
 #endif
