@@ -38,7 +38,7 @@ template <typename Real> UR3E_HD void rot_err(const Real* xmat, const Real* rv, 
 
 // cache layout: [0:3) tcp pos, [3:12) tcp mat, [12:48) J (6 rows: px,py,pz,rx,ry,rz) x 6 arm dofs, [48:54) qfrc_bias[:6]
 template <typename Real, typename D>
-UR3E_PHASE void update_cache(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s) {
+UR3E_HD void update_cache(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s) {
   int site = c.site_tcp;
   if (site < 0) return;
   int b = m.site_body[site];
@@ -73,7 +73,7 @@ UR3E_HD void pid_task(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real
 }
 
 template <typename Real, typename D>
-UR3E_PHASE void controller(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const Real* act) {
+UR3E_HD void controller(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const Real* act) {
   switch (c.ctrl_mode) {
     case CTRL_RAW: { WARP_FOR(a, m.nu) s.ctrl[a] = act[a]; break; }
     case CTRL_PD_JOINT: {
@@ -137,7 +137,7 @@ UR3E_PHASE void controller(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena
 struct ContactFlags { int grasp_count; int table_hit; };
 
 template <typename Real, typename D>
-UR3E_PHASE ContactFlags contact_flags(const DevModel<Real>& m, const EnvCfg<Real>& c, const Arena<Real, D>& s) {
+UR3E_HD ContactFlags contact_flags(const DevModel<Real>& m, const EnvCfg<Real>& c, const Arena<Real, D>& s) {
   // gym_utils.py:108-128 (distinct pad bodies touching the mug) and :174-201 (gripper subtree vs table)
   int f = 0;
   if constexpr (D::HAS_CONTACT) {
@@ -157,7 +157,7 @@ UR3E_PHASE ContactFlags contact_flags(const DevModel<Real>& m, const EnvCfg<Real
 }
 
 template <typename Real, typename D>
-UR3E_PHASE void write_obs(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const ContactFlags& cf) {
+UR3E_HD void write_obs(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const ContactFlags& cf) {
   if (c.obs_kind == OBS_STATE) {
     WARP_FOR(i, m.nq + m.nv) { if (i < 32) s.obs[i] = i < m.nq ? s.st.qpos[i] : s.st.qvel[i - m.nq]; }
   } else {
@@ -231,7 +231,7 @@ template <typename Real> UR3E_HD Real reward_v0(const Real* o, Real grip, Real h
 template <typename Real> struct StepOut { Real reward; int terminated, truncated, reason; };
 
 template <typename Real, typename D>
-UR3E_PHASE StepOut<Real> reward_done(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const ContactFlags& cf, const Real* act) {
+UR3E_HD StepOut<Real> reward_done(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const ContactFlags& cf, const Real* act) {
   StepOut<Real> r; r.reward = 0; r.terminated = 0; r.truncated = 0; r.reason = 0;
   const Real* o = s.obs;
   int t = s.st.t;
