@@ -77,7 +77,7 @@ struct Arena {
   int nd, rf0, rl0;   // dense rows [0, nd); friction rows from rf0, limit rows from rl0
   int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
   int sum_ncon, sum_nefc, sum_iter, warn;   // accumulated over the substeps of one env step
-  union {
+  union alignas(16) {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
     struct { Real lmat[D::NB][9], lpos[D::NB][3]; } kin;   // kinematics only: each body's frame relative to its parent
     Real stage[D::NPAIR][STAGE_W];   // per candidate pair: shared normal (3), then up to STAGE_PTS x (pos 3, dist 1)
@@ -182,6 +182,20 @@ template <typename Real> UR3E_HD Real sym_matvec_row(const Real* A, const Real* 
   for (int k = 0; k <= i; ++k) v += row[k] * x[k];
   for (int k = i + 1; k < n; ++k) v += A[k * (k + 1) / 2 + i] * x[k];
   return v;
+}
+// the same, fully unrolled for the size class (one address select + load + FMA per column, no loop or index arithmetic)
+template <typename Real, int N> UR3E_HD Real sym_matvec_row_n(const Real* A, const Real* x, int i, int n) {
+#if defined(__CUDA_ARCH__)
+  if (n == N) {
+    const Real* row = A + i * (i + 1) / 2;   // entries k <= i
+    const Real* col = A + i;                 // entries k > i at col[k (k + 1) / 2]
+    Real v = 0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) { const Real a = *(k <= i ? row + k : col + k * (k + 1) / 2); v += a * x[k]; }
+    return v;
+  }
+#endif
+  return sym_matvec_row(A, x, i, n);
 }
 
 // ---------------------------------------------------------------- kinematics
@@ -595,7 +609,22 @@ template <typename Real> UR3E_HD void kb_params(const Real* solref, const Real* 
 // J[r] . x for any row (dense rows read the stored Jacobian, sparse rows are one or two entries)
 template <typename Real, typename D>
 UR3E_HD Real row_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int r, const Real* x) {
-  if (r < s.nd) { const Real* J = s.u.efc_J[r]; Real v = 0; for (int k = 0; k < m.nv; ++k) v += J[k] * x[k]; return v; }
+  if (r < s.nd) {
+    const Real* J = s.u.efc_J[r];
+#if defined(__CUDA_ARCH__)
+    // float rows of the full size: five 128-bit loads (16-byte aligned rows of 80 bytes are bank-conflict free across lanes)
+    if constexpr (sizeof(Real) == 4 && D::NV % 4 == 0) {
+      if (m.nv == D::NV) {
+        const float4* J4 = reinterpret_cast<const float4*>(J);
+        float v = 0;
+#pragma unroll
+        for (int q = 0; q < D::NV / 4; ++q) { const float4 j = J4[q]; v += j.x * x[4 * q] + j.y * x[4 * q + 1] + j.z * x[4 * q + 2] + j.w * x[4 * q + 3]; }
+        return v;
+      }
+    }
+#endif
+    Real v = 0; for (int k = 0; k < m.nv; ++k) v += J[k] * x[k]; return v;
+  }
   const int t = s.efc_type[r], id = s.efc_id[r];
   if (t == ROW_EQJ) { const int d2 = m.eq_o2[id]; Real v = x[m.eq_o1[id]]; if (d2 >= 0) v -= s.eqj_deriv[id] * x[d2]; return v; }
   return t == ROW_LIMIT_HI ? -x[id] : x[id];
@@ -1037,7 +1066,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
 #endif
     // Mv, jv, and the quadratic (Gauss) part of the line cost
     WARP_FOR(i, nv + nefc) {
-      if (i < nv) s.Mv[i] = sym_matvec_row(s.M, s.search, i, nv);
+      if (i < nv) s.Mv[i] = sym_matvec_row_n<Real, D::NV>(s.M, s.search, i, nv);
       else { int r = i - nv; s.efc_jv[r] = row_dot(m, s, r, s.search); }
     }
     WARP_SYNC();
@@ -1091,7 +1120,7 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
   WARP_FOR(d, nv) s.qacc[d] = s.st.qacc_ws[d];
   WARP_SYNC();
   WARP_FOR(i, nv + nefc) {
-    if (i < nv) s.Ma[i] = sym_matvec_row(s.M, s.qacc, i, nv);
+    if (i < nv) s.Ma[i] = sym_matvec_row_n<Real, D::NV>(s.M, s.qacc, i, nv);
     else { int r = i - nv; s.efc_jar[r] = row_dot(m, s, r, s.qacc) - s.efc_aref[r]; }
   }
   WARP_SYNC();
