@@ -33,7 +33,7 @@ static int run(const HostModel& h, const double* qpos, const double* qvel, const
   SolverOpts<Real> opt{max_iter, 50, (Real)tol, (Real)(sizeof(Real) == 8 ? 1e-14 : 1e-5), (Real)(sizeof(Real) == 8 ? 1e-15 : 2e-6), (Real)(sizeof(Real) == 8 ? 0.0 : 1e-8)};
   int w = 0;
   if (nsteps == 0) forward(m, *s, opt, true);
-  for (int k = 0; k < nsteps; ++k) w |= substep(m, *s, opt);
+  for (int k = 0; k < nsteps; ++k) w |= substep(m, *s, opt, opt);
   for (int i = 0; i < h.nq; ++i) oq[i] = s->st.qpos[i];
   for (int i = 0; i < h.nv; ++i) { ov[i] = s->st.qvel[i]; oa[i] = nsteps == 0 ? s->qacc[i] : s->st.qacc_ws[i]; obias[i] = s->qfrc_bias[i]; ofc[i] = s->qfrc_constraint[i]; }
   for (int i = 0; i < h.nv; ++i) for (int j = 0; j < h.nv; ++j) { int hi = i > j ? i : j, lo = i > j ? j : i; oM[i * h.nv + j] = s->M[hi * (hi + 1) / 2 + lo]; }

@@ -27,6 +27,9 @@ struct KArgs {
   const DevModel<Real>* m;
   EnvCfg<Real> c;
   SolverOpts<Real> opt;
+  // device-memory copies of c / opt for the out-of-line cold paths (reset, redo): passing &a.c to a function would force the
+  // whole parameter block into local memory and turn every c.* / opt.* read of the hot path into a local load
+  const EnvCfg<Real>* c_dev; const SolverOpts<Real>* opt_dev;
   void* st;   // EnvState<Real, D>[n]; the lite and full size classes of a model share the record layout
   // two-tier stepping (see Batch::step): overflow hand-off from the lite kernel to the full kernel
   int* ovf_count; int* ovf_list;         // lite tier: environments whose rows / contacts exceeded the lite caps (not stored)
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
       s.cap_con = (a.cap_con > 0 && a.cap_con < D::MAXCON) ? a.cap_con : D::MAXCON; s.cap_efc = (a.cap_efc > 0 && a.cap_efc < D::MAXEFC) ? a.cap_efc : D::MAXEFC;
     }
     WARP_SYNC();
-    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim);
+    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev);
     if (a.ovf_list) {
       // lite tier: this environment needed more rows / contacts than the lite arena holds; leave its stored state
       // untouched and hand it to the full kernel
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
     const int done = r.terminated | r.truncated;
     if (done && a.final_obs && live) { WARP_FOR(i, od) a.final_obs[e * od + i] = s.obs[i]; }
     if (done && c.auto_reset) {
-      env_reset(m, c, s, a.opt, a.seed, a.env_base + (unsigned long long)e);
+      env_reset(m, *a.c_dev, s, *a.opt_dev, a.seed, a.env_base + (unsigned long long)e);
       ContactFlags cf = contact_flags(m, c, s);
       write_obs(m, c, s, cf);
     }
@@ -186,6 +189,8 @@ struct Batch : BatchBase {
   void tier_steps(int64_t* lite, int64_t* full) const override { *lite = lite_steps; *full = full_steps; }
   int64_t last_overflow() const override { return h_ovf ? *h_ovf : 0; }
   DevModel<Real>* d_model = nullptr;
+  struct DevConsts { EnvCfg<Real> c; SolverOpts<Real> opt; };
+  DevConsts* d_consts = nullptr;
   EnvState<Real, D>* d_state = nullptr;
   KArgs<Real> base;
   HostModel hm;
@@ -199,7 +204,7 @@ struct Batch : BatchBase {
   ~Batch() override {
     cudaSetDevice(device);
     cudaFree(d_ovf_count); cudaFree(d_ovf_list); if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev);
-    cudaFree(d_model); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
+    cudaFree(d_model); cudaFree(d_consts); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
   static constexpr int WPB = warps_per_block<Real, D>();
@@ -268,6 +273,9 @@ struct Batch : BatchBase {
     base.opt.rtol = f64 ? Real(1e-15) : Real(2e-6);
     base.opt.tol_improve = f64 ? Real(0) : Real(1e-8);   // MuJoCo's default solver tolerance (assets/*.xml do not override it)
     base.m = d_model; base.st = d_state; base.n = n_envs; base.env_base = (unsigned long long)cfg.env_id_base;
+    { DevConsts hc; hc.c = base.c; hc.opt = base.opt;
+      CUDA_OK(cudaMalloc(&d_consts, sizeof hc)); CUDA_OK(cudaMemcpy(d_consts, &hc, sizeof hc, cudaMemcpyHostToDevice));
+      base.c_dev = &d_consts->c; base.opt_dev = &d_consts->opt; }
     act_dim = c.act_dim; obs_dim = c.obs_dim; single_tier = cfg.single_tier != 0;
     if (cfg.lite_max_contacts > 0 && cfg.lite_max_contacts < DL::MAXCON) lite_cap_con = cfg.lite_max_contacts;
     if (cfg.lite_max_rows > 0 && cfg.lite_max_rows < DL::MAXEFC) lite_cap_efc = cfg.lite_max_rows;

@@ -717,7 +717,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
           Real j1[3], j2[3]; jac_col(m, s, d, a1, b1, j1); jac_col(m, s, d, a2, b2, j2);
           for (int r = 0; r < 3; ++r) s.u.efc_J[row + r][d] = j1[r] - j2[r];
         }
-        WARP_FOR(r, 3) { s.efc_aref[row + r] = a1[r] - a2[r]; s.efc_jv[row + r] = 0; s.efc_type[row + r] = ROW_EQ; s.efc_id[row + r] = (uint8_t)e; }
+        WARP_FOR(r, 3) { s.efc_aref[row + r] = r == 0 ? a1[0] - a2[0] : (r == 1 ? a1[1] - a2[1] : a1[2] - a2[2]); s.efc_jv[row + r] = 0; s.efc_type[row + r] = ROW_EQ; s.efc_id[row + r] = (uint8_t)e; }
         row += 3;
       } else {
         IF_LANE0 {
@@ -1262,8 +1262,9 @@ UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
 }
 
 // returns a warning mask: 1 bad qpos, 2 bad qvel, 4 bad qacc (mj_checkPos/Vel/Acc + autoreset)
+// opt_cold: the same options in addressable (device) memory, for the out-of-line redo path
 template <typename Real, typename D>
-UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
+UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, const SolverOpts<Real>& opt_cold) {
   int w = 0;
   WARP_FOR(i, m.nq + m.nv) w |= i < m.nq ? is_bad(s.st.qpos[i]) : 2 * is_bad(s.st.qvel[i - m.nq]);
   w = warp_or(w);
@@ -1272,7 +1273,7 @@ UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts
   int wa = 0;
   WARP_FOR(i, m.nv) wa |= 4 * is_bad(s.qacc[i]);
   wa = warp_or(wa);
-  if (wa) { reset_data(m, s); forward_cold(m, s, opt, true); w |= wa; }
+  if (wa) { reset_data(m, s); forward_cold(m, s, opt_cold, true); w |= wa; }
   WARP_FOR(d, m.nv) s.st.qacc_ws[d] = s.qacc[d];
   if (UR3E_BARRIERS & 16) BLOCK_SYNC(); else WARP_SYNC();
   euler(m, s);
