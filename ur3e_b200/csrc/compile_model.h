@@ -183,6 +183,15 @@ DevModel<Real> compile_model(const HostModel& h) {
     cp(m.act_ctrlrange[a], h.D("actuator_ctrlrange"), 2 * a, 2); cp(m.act_forcerange[a], h.D("actuator_forcerange"), 2 * a, 2);
     m.act_ctrllimited[a] = h.I("actuator_ctrllimited")[a]; m.act_forcelimited[a] = h.I("actuator_forcelimited")[a];
   }
+  for (int d = 0; d < h.nv; ++d) m.dof_nact[d] = 0;
+  for (int a = 0; a < h.nu; ++a) for (int k = 0; k < 2; ++k) {
+    const int d = m.act_dof[a][k];
+    if (d < 0) continue;
+    req(m.dof_nact[d] < 2, "more than two actuators on one dof");
+    m.dof_act[d][m.dof_nact[d]] = a; m.dof_actcoef[d][m.dof_nact[d]] = m.act_coef[a][k]; ++m.dof_nact[d];
+  }
+  m.ndeq = 0; m.nej = 0;
+  for (int e = 0; e < h.neq; ++e) { if (m.eq_kind[e] == EK_CONNECT) m.ndeq += 3; else m.nej += 1; }
   cp(m.qpos0, h.D("qpos0"), 0, h.nq);
   for (int k = 0; k < h.nkey; ++k) { cp(m.key_qpos[k], h.D("key_qpos"), k * h.nq, h.nq); cp(m.key_qvel[k], h.D("key_qvel"), k * h.nv, h.nv); }
   return m;

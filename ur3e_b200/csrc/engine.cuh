@@ -183,6 +183,7 @@ template <typename Real> UR3E_HD Real sym_matvec_row(const Real* A, const Real* 
   for (int k = i + 1; k < n; ++k) v += A[k * (k + 1) / 2 + i] * x[k];
   return v;
 }
+template <typename Real> UR3E_PHASE Real sym_matvec_row_cold(const Real* A, const Real* x, int i, int n) { return sym_matvec_row(A, x, i, n); }
 // the same, fully unrolled for the size class (one address select + load + FMA per column, no loop or index arithmetic)
 template <typename Real, int N> UR3E_HD Real sym_matvec_row_n(const Real* A, const Real* x, int i, int n) {
 #if defined(__CUDA_ARCH__)
@@ -195,7 +196,7 @@ template <typename Real, int N> UR3E_HD Real sym_matvec_row_n(const Real* A, con
     return v;
   }
 #endif
-  return sym_matvec_row(A, x, i, n);
+  return sym_matvec_row_cold(A, x, i, n);
 }
 
 // ---------------------------------------------------------------- kinematics
@@ -399,7 +400,7 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
     s.qfrc_bias[d] = bias;
     Real f = -m.dof_damping[d] * s.st.qvel[d];
     if (m.dof_free_k[d] < 0) f -= m.dof_stiffness[d] * (s.st.qpos[m.dof_qadr[d]] - m.dof_springref[d]);
-    for (int a = 0; a < m.nu; ++a) for (int k = 0; k < 2; ++k) if (m.act_dof[a][k] == d) f += m.act_coef[a][k] * s.act_force[a];
+    for (int k = 0; k < m.dof_nact[d]; ++k) f += m.dof_actcoef[d][k] * s.act_force[m.dof_act[d][k]];
     s.qfrc_smooth[d] = f - bias;
   }
   WARP_SYNC();
@@ -584,6 +585,11 @@ UR3E_HD void jac_col(const DevModel<Real>& m, const Arena<Real, D>& s, int d, co
   } else { out[0] = 0; out[1] = 0; out[2] = 0; }
 }
 
+// general solimp power (never taken by the reference scenes, whose power is 2): out of line so that powf stays off the hot path
+template <typename Real> UR3E_PHASE Real impedance_pow(Real x, Real s3, Real s4) {
+  if (x <= s3) return Num<Real>::pow(x, s4) / Num<Real>::pow(s3, s4 - 1);
+  return 1 - Num<Real>::pow(1 - x, s4) / Num<Real>::pow(1 - s3, s4 - 1);
+}
 template <typename Real> UR3E_HD Real impedance(const Real* si, Real pos, Real margin) {
   const Real lo = Real(0.0001), hi = Real(0.9999);
   Real s0 = rmin(rmax(si[0], lo), hi), s1 = rmin(rmax(si[1], lo), hi), s2 = rmax(si[2], Real(0)), s3 = rmin(rmax(si[3], lo), hi), s4 = rmax(si[4], Real(1));
@@ -593,8 +599,7 @@ template <typename Real> UR3E_HD Real impedance(const Real* si, Real pos, Real m
   Real y;
   if (s4 == 1) y = x;
   else if (s4 == 2) y = x <= s3 ? x * x / s3 : 1 - (1 - x) * (1 - x) / (1 - s3);
-  else if (x <= s3) y = Num<Real>::pow(x, s4) / Num<Real>::pow(s3, s4 - 1);
-  else y = 1 - Num<Real>::pow(1 - x, s4) / Num<Real>::pow(1 - s3, s4 - 1);
+  else y = impedance_pow(x, s3, s4);
   return s0 + y * (s1 - s0);
 }
 
@@ -606,6 +611,7 @@ template <typename Real> UR3E_HD void kb_params(const Real* solref, const Real* 
   } else { *K = -solref[0] / rmax(Num<Real>::minval, dmax * dmax); *B = -solref[1] / rmax(Num<Real>::minval, dmax); }
 }
 
+template <typename Real> UR3E_PHASE Real dense_dot_cold(const Real* J, const Real* x, int n) { Real v = 0; for (int k = 0; k < n; ++k) v += J[k] * x[k]; return v; }
 // J[r] . x for any row (dense rows read the stored Jacobian, sparse rows are one or two entries)
 template <typename Real, typename D>
 UR3E_HD Real row_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int r, const Real* x) {
@@ -623,7 +629,7 @@ UR3E_HD Real row_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int r, co
       }
     }
 #endif
-    Real v = 0; for (int k = 0; k < m.nv; ++k) v += J[k] * x[k]; return v;
+    return dense_dot_cold(J, x, m.nv);
   }
   const int t = s.efc_type[r], id = s.efc_id[r];
   if (t == ROW_EQJ) { const int d2 = m.eq_o2[id]; Real v = x[m.eq_o1[id]]; if (d2 >= 0) v -= s.eqj_deriv[id] * x[d2]; return v; }
@@ -646,8 +652,7 @@ template <typename Real, typename D>
 UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nv = m.nv;
   // row budget: dense rows = connect equalities + contacts (3 rows each), sparse rows = joint equalities, friction loss, limits
-  int ndeq = 0, nej = 0;
-  for (int e = 0; e < m.neq; ++e) { if (m.eq_kind[e] == EK_CONNECT) ndeq += 3; else nej += 1; }
+  const int ndeq = m.ndeq, nej = m.nej;
   const int nf = m.nfl;
   int mlo = 0, mhi = 0;   // bit d: lower / upper limit of dof d is active (dist < margin)
   WARP_FOR(d, nv) {
@@ -1172,7 +1177,7 @@ UR3E_PHASE void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
   WARP_SYNC();
 }
 
-template <typename Real> UR3E_HD int is_bad(Real x) { return !(x == x) || x > Real(1e10) || x < Real(-1e10); }
+template <typename Real> UR3E_HD int is_bad(Real x) { return !(Num<Real>::abs(x) <= Real(1e10)); }   // NaN or |x| > 1e10 (mj_checkPos/Vel/Acc)
 
 // ---------------------------------------------------------------- tree-sparse solve for the Euler step
 // (M + h diag(damping)) x = b.  M has the sparsity of the dof tree, so the reverse-order L^T D L factorisation has no
