@@ -50,6 +50,9 @@ template <typename Real, typename D> __host__ __device__ constexpr size_t arena_
 // substep phases together (block barriers in forward()), so one block per SM shares each phase's code in the I-cache.
 template <typename Real, typename D> __host__ __device__ constexpr int warps_per_block() {
   // UR3E_BLOCKS_PER_SM co-resident blocks: while one block waits at a barrier the other keeps the issue slots busy
+#ifdef UR3E_FORCE_WPB
+  return UR3E_FORCE_WPB;   // compile-only experiments (register budget at a given block size)
+#endif
   int per_sm = (int)((233472 - 1024 * UR3E_BLOCKS_PER_SM) / arena_stride<Real, D>());
   int w = per_sm / UR3E_BLOCKS_PER_SM;
   return w > UR3E_MAX_WPB ? UR3E_MAX_WPB : (w < 1 ? 1 : w);
@@ -223,6 +226,7 @@ struct Batch : BatchBase {
     const HostModel hmerged = merge_fixed_bodies(h, bmap);
     if (hmerged.nbody > D::NB) return set_err("merged model has more bodies than the kernel size class");
     DevModel<Real> m = compile_model<Real>(hmerged);
+    if (m.ndeq > 3 * D::MAXCONNECT) return set_err("model has more connect equalities than the kernel size class stores rows for");
     auto body = [&](const char* nm) { int b = h.name2id(OBJ_BODY, nm); return b >= 0 ? bmap[b] : -1; };
     CUDA_OK(cudaMalloc(&d_model, sizeof m)); CUDA_OK(cudaMemcpy(d_model, &m, sizeof m, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMalloc(&d_state, sizeof(EnvState<Real, D>) * n_envs)); CUDA_OK(cudaMemset(d_state, 0, sizeof(EnvState<Real, D>) * n_envs));

@@ -18,7 +18,8 @@ struct Dims {
   static constexpr bool HAS_CONTACT = MAXCON_ > 0;
   static constexpr int NS = MAXSITE;
   static constexpr int NGRP = MAXEQ + NPAIR;
-  static constexpr int MAXDENSE = HAS_CONTACT ? 3 * MAXEQ + 3 * MAXCON : 1;   // stored Jacobian rows
+  static constexpr int MAXCONNECT = 2;   // connect equalities a size class stores rows for (the 2F85 has two; checked at batch creation)
+  static constexpr int MAXDENSE = HAS_CONTACT ? 3 * MAXCONNECT + 3 * MAXCON : 1;   // stored Jacobian rows
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // body counts are after fixed-body merging (merge_bodies.h)          // assets/ur3e_raw.xml
 using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 16, 64>;    // assets/ur3e_2f85.xml
@@ -55,15 +56,19 @@ struct Arena {
     struct { Real xmat[D::NB][9], xipos[D::NB][3]; } k;
     struct { Real H[(D::NV + 1) * (D::NV + 2) / 2]; } n;   // augmented Newton / Euler matrix, packed lower triangle: (i,j) at i(i+1)/2 + j
   } fr;
-  union { alignas(16) Real colbuf[2][32]; Real obs[32]; };   // solver scratch / the step's observation (written after the last solve)
-  Real dinv[D::NV];
+  union { alignas(16) Real colbuf[1][32]; Real obs[32]; };   // solver scratch / the step's observation (written after the last solve)
   Real cdof[D::NV][6];
   Real M[D::NV * (D::NV + 1) / 2];   // packed lower triangle, M(i,j) at i(i+1)/2 + j for j <= i
-  Real qfrc_smooth[D::NV], qfrc_bias[D::NV], qfrc_constraint[D::NV], grad[D::NV], search[D::NV], Ma[D::NV], Mv[D::NV];
-  Real geom_xpos[D::NG][3], geom_xmat[D::NG][9], site_xpos[D::NS][3], site_xmat[1][9] /* tcp only */, site_velp[D::NS][3];
+  Real qfrc_smooth[D::NV], qfrc_bias[D::NV], qfrc_constraint[D::NV], grad[D::NV], search[D::NV], Ma[D::NV];
+  union { Real Mv[D::NV]; Real dinv[D::NV]; };   // M * search (line search) / reciprocal pivots of the shared-memory factorisations (host build, tree LDL)
+  Real site_xpos[D::NS][3], site_xmat[1][9] /* tcp only */, site_velp[D::NS][3];
   Real con_pos[D::MAXCON][3], con_dist[D::MAXCON], con_mu[D::MAXCON];
   union { Real frame[D::MAXCON][9]; Real H[D::MAXCON][6]; } cu;   // contact frames (row assembly) / cone Hessians (solver)
-  Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_force[D::MAXEFC], efc_jar[D::MAXEFC], efc_jv[D::MAXEFC], efc_Dact[D::MAXEFC];
+  Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_jv[D::MAXEFC], efc_Dact[D::MAXEFC];
+  union {   // geom frames are dead once the contacts exist; the solver's force / residual vectors reuse their storage
+    struct { Real efc_force[D::MAXEFC], efc_jar[D::MAXEFC]; };
+    struct { Real geom_xpos[D::NG][3], geom_xmat[D::NG][9]; };
+  };
   uint8_t con_pair[D::MAXCON], con_row[D::MAXCON];
   uint8_t efc_type[D::MAXEFC], efc_id[D::MAXEFC];
   // row groups sharing one column set (a connect equality, the joint equality, the contacts of one geom pair)
@@ -1044,7 +1049,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
       const int r0 = s.grp_row0[g], r1 = r0 + s.grp_nrow[g], mask = s.grp_mask[g], kc = popcount32(mask);
       const bool contact = s.efc_type[r0] >= ROW_CON_N;
       // column list of the group: cols[k] = index of the k-th set bit of its dof mask (solver scratch; __fns is a slow software loop)
-      uint8_t* cols = reinterpret_cast<uint8_t*>(s.colbuf[1]);
+      uint8_t* cols = reinterpret_cast<uint8_t*>(s.colbuf[0]);
       WARP_FOR(d, 32) if ((mask >> d) & 1) cols[popcount32(mask & (int)((1u << d) - 1u))] = (uint8_t)d;
       WARP_SYNC();
       WARP_FOR(e, kc * (kc + 1) / 2) {
