@@ -22,9 +22,9 @@ struct Dims {
   static constexpr int MAXDENSE = HAS_CONTACT ? 3 * MAXCONNECT + 3 * MAXCON : 1;   // stored Jacobian rows
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // body counts are after fixed-body merging (merge_bodies.h)          // assets/ur3e_raw.xml
-using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 16, 64>;    // assets/ur3e_2f85.xml
+using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 15, 64>;    // assets/ur3e_2f85.xml
 using DimsMain = Dims<19, 20, 21, 7, 7, 13, 24, 96>;   // assets/main.xml
-using DimsMainLite = Dims<19, 20, 21, 7, 7, 13, 8, 48>;   // same model, caps for the common case (<= 8 contacts, <= 48 rows)
+using DimsMainLite = Dims<19, 20, 21, 7, 7, 13, 8, 44>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 constexpr int STAGE_W = 3 + 4 * STAGE_PTS;
@@ -77,11 +77,11 @@ struct Arena {
   uint8_t stage_n[D::NPAIR], stage_off[D::NPAIR];
   Real eqj_deriv[MAXEQ];
   // per dof: its sparse rows (255 = none) so that the solver's inner loops never touch the model tables
-  Real sp_ejc[D::NV];
   uint8_t sp_fl[D::NV], sp_lo[D::NV], sp_hi[D::NV], sp_ej[D::NV];
-  int nd, rf0, rl0;   // dense rows [0, nd); friction rows from rf0, limit rows from rl0
-  int ncon, nefc, ne, nf, nl, ngrp, lim_lo, lim_hi, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
-  int sum_ncon, sum_nefc, sum_iter, warn;   // accumulated over the substeps of one env step
+  int lim_lo, lim_hi;
+  short nd, rf0, rl0;   // dense rows [0, nd); friction rows from rf0, limit rows from rl0
+  short ncon, nefc, ne, nf, nl, ngrp, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
+  short sum_ncon, sum_nefc, sum_iter, warn;   // accumulated over the substeps of one env step
   union alignas(16) {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
     struct { Real lmat[D::NB][9], lpos[D::NB][3]; } kin;   // kinematics only: each body's frame relative to its parent
@@ -640,13 +640,19 @@ UR3E_HD Real row_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int r, co
   if (t == ROW_EQJ) { const int d2 = m.eq_o2[id]; Real v = x[m.eq_o1[id]]; if (d2 >= 0) v -= s.eqj_deriv[id] * x[d2]; return v; }
   return t == ROW_LIMIT_HI ? -x[id] : x[id];
 }
+// entry of joint-equality row r in column d (d is one of the row's two dofs): 1 on the first dof, -polynomial derivative on the second
+template <typename Real, typename D>
+UR3E_HD Real eqj_coef(const DevModel<Real>& m, const Arena<Real, D>& s, int d, int r) {
+  const int id = s.efc_id[r];
+  return m.eq_o1[id] == d ? Real(1) : -s.eqj_deriv[id];
+}
 // sum_r J[r][d] f[r] over all rows
 template <typename Real, typename D>
 UR3E_HD Real col_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int d, const Real* f) {
   (void)m;
   Real v = 0;
   for (int r = 0; r < s.nd; ++r) v += s.u.efc_J[r][d] * f[r];
-  int r = s.sp_ej[d]; if (r != 255) v += s.sp_ejc[d] * f[r];
+  int r = s.sp_ej[d]; if (r != 255) v += eqj_coef(m, s, d, r) * f[r];
   r = s.sp_fl[d]; if (r != 255) v += f[r];
   r = s.sp_lo[d]; if (r != 255) v += f[r];
   r = s.sp_hi[d]; if (r != 255) v -= f[r];
@@ -711,7 +717,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
     s.sp_lo[d] = (uint8_t)((((mlo >> d) & 1) && r < nefc) ? r : 255);
     if ((mlo >> d) & 1) ++r;
     s.sp_hi[d] = (uint8_t)((((mhi >> d) & 1) && r < nefc) ? r : 255);
-    s.sp_ej[d] = 255; s.sp_ejc[d] = 0;
+    s.sp_ej[d] = 255;
   }
   WARP_SYNC();
   // rows: efc_aref temporarily holds pos, efc_jv holds margin
@@ -740,7 +746,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
             deriv = c[1] + p2 * (2 * c[2] + p2 * (3 * c[3] + p2 * 4 * c[4]));
           } else pos = p1 - c[0];
           s.eqj_deriv[e] = deriv;
-          if (rj < nefc) { s.sp_ej[d1] = (uint8_t)rj; s.sp_ejc[d1] = 1; if (d2 >= 0) { s.sp_ej[d2] = (uint8_t)rj; s.sp_ejc[d2] = -deriv; } }
+          if (rj < nefc) { s.sp_ej[d1] = (uint8_t)rj; if (d2 >= 0) s.sp_ej[d2] = (uint8_t)rj; }
           if (rj < D::MAXEFC) { s.efc_aref[rj] = pos; s.efc_jv[rj] = 0; s.efc_type[rj] = ROW_EQJ; s.efc_id[rj] = (uint8_t)e; }
         }
         rj += 1;
@@ -1038,7 +1044,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
             r = s.sp_hi[a]; if (r != 255) h += s.efc_Dact[r];
           }
           const int ra = s.sp_ej[a];   // joint equality: D [c_a c_b] on its two dofs
-          if (ra != 255 && ra == s.sp_ej[b]) h += s.efc_Dact[ra] * s.sp_ejc[a] * s.sp_ejc[b];
+          if (ra != 255 && ra == s.sp_ej[b]) h += s.efc_Dact[ra] * eqj_coef(m, s, a, ra) * eqj_coef(m, s, b, ra);
           s.fr.n.H[e] = h;
         }
       }
