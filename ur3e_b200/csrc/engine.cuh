@@ -22,7 +22,7 @@ struct Dims {
   static constexpr int MAXDENSE = HAS_CONTACT ? 3 * MAXCONNECT + 3 * MAXCON : 1;   // stored Jacobian rows
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // body counts are after fixed-body merging (merge_bodies.h)          // assets/ur3e_raw.xml
-using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 15, 64>;    // assets/ur3e_2f85.xml
+using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 12, 56>;    // assets/ur3e_2f85.xml
 using DimsMain = Dims<19, 20, 21, 7, 7, 13, 24, 96>;   // assets/main.xml
 using DimsMainLite = Dims<19, 20, 21, 7, 7, 13, 8, 44>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
 
