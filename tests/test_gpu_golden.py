@@ -102,6 +102,20 @@ def test_controller_entry_points_track_targets():
     assert controller.task_space.pid_task_ctrl is controller.move_l.run
 
 
+def test_device_built_per_env_trajectories_drive_move_l():
+    """build_traj on the device -> [T, N, 7] per-environment waypoint streams -> the batched move_l loop, no host round trip."""
+    tcp = torch.tensor([0.29799994, 0.13349916, 0.1682003], device="cuda", dtype=torch.float64)
+    rot = torch.tensor(presets.TOOL_ROTVEC, device="cuda", dtype=torch.float64)
+    off = torch.tensor([[0.03, 0.02, 0.03], [-0.02, 0.03, 0.02], [0.0, -0.03, 0.04], [0.02, 0.0, -0.01]], device="cuda", dtype=torch.float64)
+    start = torch.cat([tcp.expand(4, 3), rot.expand(4, 3), torch.zeros(4, 1, device="cuda", dtype=torch.float64)], dim=1)
+    stop = start.clone(); stop[:, :3] += off
+    traj = controller.build_traj.build_traj_l_point_custom(start, stop, hold=100)                      # [1500, 4, 7] on the GPU
+    assert traj.is_cuda and traj.shape == (1500, 4, 7)
+    q, v, b = controller.move_l.run(traj, n_envs=4, record_every=1500)
+    for e in range(4):
+        assert np.abs(b.debug_forward(e)["tcp_pos"] - stop[e, :3].cpu().numpy()).max() < 0.02
+
+
 def test_two_tier_stepping_f32():
     """float32 main.xml batches step with the lite size class and hand environments that exceed its caps (built-in: 8 contacts
     / 40 rows; lowered to 4 contacts here so that the fixture's grasp, 5-6 contacts, overflows) to the full class inside the
