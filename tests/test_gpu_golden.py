@@ -111,7 +111,8 @@ def test_device_built_per_env_trajectories_drive_move_l():
     stop = start.clone(); stop[:, :3] += off
     traj = controller.build_traj.build_traj_l_point_custom(start, stop, hold=100)                      # [1500, 4, 7] on the GPU
     assert traj.is_cuda and traj.shape == (1500, 4, 7)
-    q, v, b = controller.move_l.run(traj, n_envs=4, record_every=1500)
+    traj = torch.cat([traj, traj[-1:].expand(1000, 4, 7)])                                              # settle on the last waypoint
+    q, v, b = controller.move_l.run(traj, n_envs=4, record_every=2500)
     for e in range(4):
         assert np.abs(b.debug_forward(e)["tcp_pos"] - stop[e, :3].cpu().numpy()).max() < 0.02
 

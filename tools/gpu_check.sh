@@ -1,7 +1,7 @@
 #!/bin/bash
 # GPU box helper: parity tests, then the three bench workloads (kernel-only lines).  usage: tools/gpu_check.sh [tag]
 tag=${1:-chk}
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q 2>&1 | tail -1
 for w in rollout mug reach; do
   python bench.py --workload $w --no-cpu-baseline --no-e2e > gpurun_out/${tag}_$w.json 2> gpurun_out/${tag}_$w.err || { echo "$w FAILED"; tail -3 gpurun_out/${tag}_$w.err; continue; }
   python -c "

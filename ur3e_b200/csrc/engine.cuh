@@ -1031,21 +1031,26 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
     // converged: MuJoCo's scaled-gradient test, or the gradient is at the rounding floor of its own terms
     if (scale * Num<Real>::sqrt(gg) < opt.tol || gg < opt.rtol * opt.rtol * gref) return 1;
     // H = M + J^T diag(Dact) J + cone blocks ; augmented row = -grad.
-    // phase A: M, the single-column rows (friction loss, limits) and the rhs row
+    // phase A: M and the rhs row (plain copies), then the rows with one or two entries: friction loss / limits / the joint
+    // equality's squares on the diagonal (lane = dof) and the joint equality's single off-diagonal entry (lane = equality)
     {
-      WARP_FOR(e, (nv + 1) * (nv + 2) / 2) {
-        int ab = m.tri_ab[e], a = ab >> 8, b = ab & 255;   // (a, b), b <= a, over the (nv+1) x (nv+1) lower triangle
-        if (a == nv) { if (b < nv) s.fr.n.H[e] = -s.grad[b]; }
-        else {
-          Real h = s.M[e];
-          if (a == b) {
-            int r = s.sp_fl[a]; if (r != 255) h += s.efc_Dact[r];
-            r = s.sp_lo[a]; if (r != 255) h += s.efc_Dact[r];
-            r = s.sp_hi[a]; if (r != 255) h += s.efc_Dact[r];
+      const int ntri = nv * (nv + 1) / 2;
+      WARP_FOR(e, ntri + nv) s.fr.n.H[e] = e < ntri ? s.M[e] : -s.grad[e - ntri];
+      WARP_SYNC();
+      WARP_FOR(i, nv + m.neq) {
+        if (i < nv) {
+          Real h = 0;
+          int r = s.sp_fl[i]; if (r != 255) h += s.efc_Dact[r];
+          r = s.sp_lo[i]; if (r != 255) h += s.efc_Dact[r];
+          r = s.sp_hi[i]; if (r != 255) h += s.efc_Dact[r];
+          r = s.sp_ej[i]; if (r != 255) { const Real c = eqj_coef(m, s, i, r); h += s.efc_Dact[r] * c * c; }
+          s.fr.n.H[i * (i + 1) / 2 + i] += h;
+        } else {
+          const int e = i - nv;
+          if (m.eq_kind[e] != EK_CONNECT && m.eq_o2[e] >= 0) {
+            const int d1 = m.eq_o1[e], d2 = m.eq_o2[e], r = s.sp_ej[d1], hi = d1 > d2 ? d1 : d2, lo = d1 > d2 ? d2 : d1;
+            if (r != 255 && r == s.sp_ej[d2] && s.efc_id[r] == e) s.fr.n.H[hi * (hi + 1) / 2 + lo] -= s.efc_Dact[r] * s.eqj_deriv[e];
           }
-          const int ra = s.sp_ej[a];   // joint equality: D [c_a c_b] on its two dofs
-          if (ra != 255 && ra == s.sp_ej[b]) h += s.efc_Dact[ra] * eqj_coef(m, s, a, ra) * eqj_coef(m, s, b, ra);
-          s.fr.n.H[e] = h;
         }
       }
       WARP_SYNC();
