@@ -651,6 +651,7 @@ template <typename Real, typename D>
 UR3E_HD Real col_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int d, const Real* f) {
   (void)m;
   Real v = 0;
+#pragma unroll 4
   for (int r = 0; r < s.nd; ++r) v += s.u.efc_J[r][d] * f[r];
   int r = s.sp_ej[d]; if (r != 255) v += eqj_coef(m, s, d, r) * f[r];
   r = s.sp_fl[d]; if (r != 255) v += f[r];
