@@ -190,6 +190,13 @@ DevModel<Real> compile_model(const HostModel& h) {
     req(m.dof_nact[d] < 2, "more than two actuators on one dof");
     m.dof_act[d][m.dof_nact[d]] = a; m.dof_actcoef[d][m.dof_nact[d]] = m.act_coef[a][k]; ++m.dof_nact[d];
   }
+  m.split = h.nv;
+  if (h.nv > 0) {
+    const int last_root = root[dbody[h.nv - 1]];
+    int s0 = h.nv - 1;
+    while (s0 > 0 && root[dbody[s0 - 1]] == last_root) --s0;
+    if (s0 > 0) m.split = s0;   // dofs [s0, nv) form the last tree; dofs are numbered tree by tree, so nothing before s0 shares it
+  }
   m.ndeq = 0; m.nej = 0;
   for (int e = 0; e < h.neq; ++e) { if (m.eq_kind[e] == EK_CONNECT) m.ndeq += 3; else m.nej += 1; }
   cp(m.qpos0, h.D("qpos0"), 0, h.nq);

@@ -75,6 +75,7 @@ struct DevModel {
   // actuators: force = gain*ctrl + b0 + b1*len + b2*vel ; moment over at most two dofs
   int act_dof[MAXU][2], act_ctrllimited[MAXU], act_forcelimited[MAXU];
   int dof_nact[MAXV], dof_act[MAXV][2]; Real dof_actcoef[MAXV][2];   // transposed transmission: the (at most two) actuators acting on each dof
+  int split;       // first dof of the last kinematic tree when the model has more than one (else nv): M is block diagonal across it
   int ndeq, nej;   // rows of the connect equalities (3 each) / number of joint equalities
   Real act_coef[MAXU][2], act_gain[MAXU], act_bias[MAXU][3], act_ctrlrange[MAXU][2], act_forcerange[MAXU][2];
   // reset

@@ -11,8 +11,11 @@
 
 namespace ur3e {
 
-template <int NB_, int NV_, int NQ_, int NU_, int NG_, int NPAIR_, int MAXCON_, int MAXEFC_>
+template <int NB_, int NV_, int NQ_, int NU_, int NG_, int NPAIR_, int MAXCON_, int MAXEFC_, int SPLIT_ = NV_>
 struct Dims {
+  // dofs [SPLIT, NV) belong to the model's last kinematic tree (the mug's free joint): M never couples them to the dofs
+  // before, and the Newton matrix only does while a constraint spans both (a pad touching the mug) -- see chol_solve_reg_body
+  static constexpr int SPLIT = SPLIT_;
   static constexpr int NB = NB_, NV = NV_, NQ = NQ_, NU = NU_, NG = NG_ > 0 ? NG_ : 1, NPAIR = NPAIR_ > 0 ? NPAIR_ : 1;
   static constexpr int MAXCON = MAXCON_ > 0 ? MAXCON_ : 1, MAXEFC = MAXEFC_ > 0 ? MAXEFC_ : 1;
   static constexpr bool HAS_CONTACT = MAXCON_ > 0;
@@ -23,8 +26,8 @@ struct Dims {
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // body counts are after fixed-body merging (merge_bodies.h)          // assets/ur3e_raw.xml
 using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 12, 56>;    // assets/ur3e_2f85.xml
-using DimsMain = Dims<19, 20, 21, 7, 7, 13, 24, 96>;   // assets/main.xml
-using DimsMainLite = Dims<19, 20, 21, 7, 7, 13, 8, 44>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
+using DimsMain = Dims<19, 20, 21, 7, 7, 13, 24, 96, 14>;   // assets/main.xml
+using DimsMainLite = Dims<19, 20, 21, 7, 7, 13, 8, 44, 14>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 constexpr int STAGE_W = 3 + 4 * STAGE_PTS;
@@ -82,6 +85,7 @@ struct Arena {
   short nd, rf0, rl0;   // dense rows [0, nd); friction rows from rf0, limit rows from rl0
   short ncon, nefc, ne, nf, nl, ngrp, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
   short sum_ncon, sum_nefc, sum_iter, warn;   // accumulated over the substeps of one env step
+  short coupled;   // some constraint of this substep has entries on both sides of Dims::SPLIT
   union alignas(16) {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
     struct { Real lmat[D::NB][9], lpos[D::NB][3]; } kin;   // kinematics only: each body's frame relative to its parent
@@ -689,12 +693,16 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   int nefc = rl0 + nl;
   if (nefc > cape) { nefc = cape; IF_LANE0 s.overflow |= 2; }
   // row groups: dense rows that share one column set (used by the Hessian assembly)
-  int ngrp = 0;
+  int ngrp = 0, coupled = 0;
+  const int lowmask = (int)((1u << m.split) - 1u);
+  auto spans = [lowmask](int mask) { return (mask & lowmask) != 0 && (mask & ~lowmask) != 0; };
+  for (int e = 0; e < m.neq; ++e) if (m.eq_kind[e] != EK_CONNECT && m.eq_o2[e] >= 0) coupled |= spans((1 << m.eq_o1[e]) | (1 << m.eq_o2[e]));
   {
     int row = 0;
     for (int e = 0; e < m.neq; ++e) if (m.eq_kind[e] == EK_CONNECT) {
       const int mask = (int)(m.body_dofmask[m.eq_o1[e]] | m.body_dofmask[m.eq_o2[e]]);
       IF_LANE0 { s.grp_row0[ngrp] = (uint8_t)row; s.grp_nrow[ngrp] = 3; s.grp_mask[ngrp] = mask; }
+      coupled |= spans(mask);
       ++ngrp; row += 3;
     }
     if constexpr (D::HAS_CONTACT) {
@@ -704,13 +712,14 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
         if (p != prev) {
           const int mask = (int)(m.body_dofmask[m.geom_body[m.pair_g1[p]]] ^ m.body_dofmask[m.geom_body[m.pair_g2[p]]]);
           IF_LANE0 { s.grp_row0[ngrp] = (uint8_t)(base_c + 3 * c); s.grp_nrow[ngrp] = 0; s.grp_mask[ngrp] = mask; }
+          coupled |= spans(mask);
           ++ngrp; prev = p;
         }
         IF_LANE0 s.grp_nrow[ngrp - 1] += 3;
       }
     }
   }
-  IF_LANE0 { s.ne = ndeq + nej; s.nf = nf; s.nl = nl; s.nefc = nefc; s.ngrp = ngrp; s.lim_lo = mlo; s.lim_hi = mhi; s.nd = nd; s.rf0 = rf0; s.rl0 = rl0; }
+  IF_LANE0 { s.coupled = (short)coupled; s.ne = ndeq + nej; s.nf = nf; s.nl = nl; s.nefc = nefc; s.ngrp = ngrp; s.lim_lo = mlo; s.lim_hi = mhi; s.nd = nd; s.rf0 = rf0; s.rl0 = rl0; }
   WARP_FOR(d, nv) {
     const int k = m.dof_flrow[d], below = (1 << d) - 1;
     int r = rl0 + popcount32(mlo & below) + popcount32(mhi & below);
@@ -898,8 +907,11 @@ UR3E_PHASE void chol_solve_aug(Arena<Real, D>& s, int n, Real* x) {
 #define UR3E_REG_CHOL 1
 #endif
 #if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
-template <typename Real, int N>
-__device__ __forceinline__ void chol_solve_reg_body(Real* tri, Real* rhs, int n, Real* x) {
+// `coupled` = false promises that the block [S, N) x [0, S) of the matrix is exactly zero: the updates of the columns >= S
+// by the steps k < S are then exact no-ops for every row (and for the right-hand side) and are skipped -- 84 of the 190
+// shuffle + FMA pairs for main.xml with the mug resting (S = 14).
+template <typename Real, int N, int S = N>
+__device__ __forceinline__ void chol_solve_reg_body(Real* tri, Real* rhs, int n, Real* x, bool coupled = true) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = UR3E_LANE;
   const bool isrow = lane < n, isrhs = lane == N;
@@ -917,8 +929,17 @@ __device__ __forceinline__ void chol_solve_reg_body(Real* tri, Real* rhs, int n,
     Real d = __shfl_sync(FULL, a[k], k);
     d = d > Num<Real>::minval ? d : Num<Real>::minval;
     const Real t = a[k] * (Real(1) / d);
+    if (k < S) {
 #pragma unroll
-    for (int j = k + 1; j < N; ++j) a[j] -= t * __shfl_sync(FULL, a[k], j);
+      for (int j = k + 1; j < S; ++j) a[j] -= t * __shfl_sync(FULL, a[k], j);
+      if (coupled) {
+#pragma unroll
+        for (int j = S; j < N; ++j) a[j] -= t * __shfl_sync(FULL, a[k], j);
+      }
+    } else {
+#pragma unroll
+      for (int j = k + 1; j < N; ++j) a[j] -= t * __shfl_sync(FULL, a[k], j);
+    }
     if (k < jmax || (isrhs && k == jmax)) row[k] = t;   // strictly-lower L entries, all of w; stored at once, which frees the register
   }
   __syncwarp();
@@ -932,8 +953,8 @@ __device__ __forceinline__ void chol_solve_reg_body(Real* tri, Real* rhs, int n,
   if (lane < n) x[lane] = xi;
   __syncwarp();
 }
-template <typename Real, int N>
-__device__ __noinline__ void chol_solve_reg(Real* tri, Real* rhs, int n, Real* x) { chol_solve_reg_body<Real, N>(tri, rhs, n, x); }
+template <typename Real, int N, int S>
+__device__ __noinline__ void chol_solve_reg(Real* tri, Real* rhs, int n, Real* x, bool coupled) { chol_solve_reg_body<Real, N, S>(tri, rhs, n, x, coupled); }
 #endif
 
 // ---------------------------------------------------------------- Newton solver on the primal problem
@@ -1082,7 +1103,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
       WARP_SYNC();
     }
 #if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
-    chol_solve_reg_body<Real, D::NV>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.search);   // inlined in the Newton loop; the Euler step and the unconstrained case share the out-of-line copy
+    chol_solve_reg_body<Real, D::NV, D::SPLIT>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.search, s.coupled != 0 || m.split != D::SPLIT);   // inlined in the Newton loop; the Euler step and the unconstrained case share the out-of-line copy
 #else
     chol_solve_aug(s, nv, s.search);
 #endif
@@ -1131,7 +1152,7 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
     WARP_FOR(d, nv) s.qfrc_constraint[d] = 0;
     WARP_SYNC();
 #if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
-    chol_solve_reg<Real, D::NV>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.qacc);
+    chol_solve_reg<Real, D::NV, D::SPLIT>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.qacc, m.split != D::SPLIT);   // H = M here
 #else
     chol_solve_aug(s, nv, s.qacc);
 #endif
@@ -1255,7 +1276,7 @@ UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
     // M is dead after this step (the next substep rebuilds it), so the damping goes onto its diagonal in place
     WARP_FOR(d, nv) { s.M[d * (d + 1) / 2 + d] += h * m.dof_damping[d]; s.search[d] = s.qfrc_smooth[d] + s.qfrc_constraint[d]; }
     WARP_SYNC();
-    chol_solve_reg<Real, D::NV>(s.M, s.search, nv, s.search);
+    chol_solve_reg<Real, D::NV, D::SPLIT>(s.M, s.search, nv, s.search, m.split != D::SPLIT);   // M + h B never couples two trees
 #else
     Real* A = s.fr.n.H;
     WARP_FOR(e, nv * (nv + 1) / 2) { const int ab = m.tri_ab[e]; A[e] = s.M[e] + ((ab >> 8) == (ab & 255) ? h * m.dof_damping[ab >> 8] : Real(0)); }
