@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
   const int od = c.obs_dim;
   long long count = a.n; int iters = 1;
   if (a.list) { count = *a.list_count; const long long per = (long long)gridDim.x * WPB; iters = (int)((count + per - 1) / per); }
+#ifdef UR3E_PERSISTENT
+  else { const long long per = (long long)gridDim.x * WPB; iters = (int)((count + per - 1) / per); }   // A/B: resident grid, strided environments
+#endif
   for (int it = 0; it < iters; ++it) {
     const long long idx = ((long long)it * gridDim.x + blockIdx.x) * WPB + warp;
     const bool live = idx < count;
@@ -345,7 +348,11 @@ struct Batch : BatchBase {
       } else {
         constexpr int WL = warps_per_block<Real, DL>();
         KArgs<Real> l = a; l.ovf_count = d_ovf_count; l.ovf_list = d_ovf_list; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc;
-        if (int rc = launch_step<DL>(l, s, (unsigned)((n + WL - 1) / WL))) return rc;
+        unsigned lite_blocks = (unsigned)((n + WL - 1) / WL);
+#ifdef UR3E_PERSISTENT
+        if (lite_blocks > (unsigned)(UR3E_BLOCKS_PER_SM * sm_count)) lite_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count);
+#endif
+        if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
         a.list_count = d_ovf_count; a.list = d_ovf_list;
         unsigned tail_blocks = (unsigned)(2 * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;
         if (int rc = launch_step<D>(a, s, tail_blocks)) return rc;
