@@ -231,3 +231,27 @@ def test_state_roundtrip_and_determinism(assets):
         assert torch.equal(x1, x2)
     o3 = b2.reset(seed=12)
     assert not torch.equal(o3[:, 3:5], o2[:, 3:5])                    # a different seed draws different mug positions
+
+
+def test_model_smaller_than_its_size_class_f64(assets, tmp_path):
+    """A 5-dof arm (ur3e_raw.xml without its last joint and motor) runs in the 6-dof size class: the register-resident
+    solve pads the missing row with an identity row, the unrolled mat-vec / row dots take their generic fall-backs."""
+    src = open(assets + "/ur3e_raw.xml").read().split("\n")
+    src = [ln for ln in src if "wrist_3_joint" not in ln]          # drops the joint and its motor; the link stays, welded to wrist_2
+    path = str(tmp_path / "ur3e_5dof.xml")
+    open(path, "w").write("\n".join(src))
+    m = Model(path)
+    assert (m.nv, m.nu) == (5, 5)
+    om = O.Model(path); d = O.Data(om)
+    b = SimBatch(m, env_config(ctrl_mode=lib.CTRL_RAW, obs_kind=lib.OBS_STATE, obs_dim=10, act_dim=5), 2, 0, torch.float64)
+    b.reset()
+    d.reset()
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for k in range(600):
+        u = rng.uniform(-3, 3, 5) if k % 50 == 0 else u
+        d.ctrl[:] = u; d.step(1)
+        obs, *_ = b.step(torch.tensor(np.tile(u, (2, 1)), dtype=torch.float64, device="cuda"))
+        o = obs[0].cpu().numpy()
+        worst = max(worst, rel(o[:5], d.qpos), rel(o[5:], d.qvel))
+    assert worst < 1e-9, worst
