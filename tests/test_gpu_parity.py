@@ -182,6 +182,24 @@ def test_host_entry_point(assets):
     assert np.isfinite(obs).all() and np.abs(obs[:, :3] - o0[:, :3]).max() < 1e-2
 
 
+def test_host_entry_point_chunked_pipeline_matches_device_path(assets):
+    """Batches >= 16384 environments go through the host entry point in four ranges on two streams (copies overlap the
+    stepping); every environment's result is bit-identical to the single-launch device path, incl. a ragged last range."""
+    n = 16384 + 77
+    cfg = dict(ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2, reset_key=1,
+               term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500, reset_noise=lib.NOISE_HIGH, auto_reset=1)
+    bh = make(assets, "main.xml", n, torch.float32, **cfg); bd = make(assets, "main.xml", n, torch.float32, **cfg)
+    o0 = bh.reset(seed=5); assert torch.equal(o0, bd.reset(seed=5))
+    rng = np.random.default_rng(0)
+    obs = np.zeros((n, 24), np.float32); rew = np.zeros(n, np.float32); te = np.zeros(n, np.uint8); tr = np.zeros(n, np.uint8)
+    for k in range(3):
+        a = np.ascontiguousarray(np.hstack([o0[:, :3].cpu().numpy() + rng.uniform(-0.05, 0.05, (n, 3)), rng.uniform(0, 1, (n, 1))]).astype(np.float32))
+        bh.step_host(a, obs, rew, te, tr)
+        od, rd, ted, trd = bd.step(torch.tensor(a, device="cuda"))
+        assert np.array_equal(obs, od.cpu().numpy()) and np.array_equal(rew, rd.cpu().numpy())
+        assert np.array_equal(te, ted.cpu().numpy()) and np.array_equal(tr, trd.cpu().numpy())
+
+
 def test_bad_state_autoreset_and_masked_reset(assets):
     """mj_checkPos/Vel autoreset (MUJOCO_LOG.TXT): an environment with NaN / huge state is reset to qpos0 inside the
     step and counted; the others are untouched.  Masked reset only touches the selected environments."""

@@ -191,7 +191,7 @@ struct Batch : BatchBase {
   static constexpr bool HAS_LITE = !std::is_same<D, DL>::value;
   static_assert(sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DL>), "lite and full size classes must share the record layout");
   int *d_ovf_count = nullptr, *d_ovf_list = nullptr, *h_ovf = nullptr; cudaEvent_t ovf_ev = nullptr; bool ovf_pending = false, heavy = false;
-  long long lite_steps = 0, full_steps = 0; bool single_tier = false; int lite_cap_con = DL::MAXCON, lite_cap_efc = DL::MAXEFC;
+  long long lite_steps = 0, full_steps = 0, ovf_of = 1; bool single_tier = false; int lite_cap_con = DL::MAXCON, lite_cap_efc = DL::MAXEFC;
   void tier_steps(int64_t* lite, int64_t* full) const override { *lite = lite_steps; *full = full_steps; }
   int64_t last_overflow() const override { return h_ovf ? *h_ovf : 0; }
   DevModel<Real>* d_model = nullptr;
@@ -203,7 +203,7 @@ struct Batch : BatchBase {
   int act_dim = 0, obs_dim = 0;
   // staging for the host-buffer entry point
   Real *d_act = nullptr, *d_obs = nullptr, *d_rew = nullptr; uint8_t *d_term = nullptr, *d_trunc = nullptr; double* d_dbg = nullptr;
-  cudaStream_t own_stream = nullptr;
+  cudaStream_t own_stream = nullptr, own_stream2 = nullptr;
   uint64_t seed = 0;
   int sm_count = 148;
 
@@ -212,6 +212,7 @@ struct Batch : BatchBase {
     cudaFree(d_ovf_count); cudaFree(d_ovf_list); if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev);
     cudaFree(d_model); cudaFree(d_consts); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
     if (own_stream) cudaStreamDestroy(own_stream);
+    if (own_stream2) cudaStreamDestroy(own_stream2);
   }
   static constexpr int WPB = warps_per_block<Real, D>();
   int launch(KArgs<Real>& a, cudaStream_t s, long long envs) {
@@ -296,7 +297,7 @@ struct Batch : BatchBase {
     if constexpr (HAS_LITE) {
       constexpr int WL = warps_per_block<Real, DL>();
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
-      CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int))); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
+      CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int) * HOST_CHUNKS)); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
       CUDA_OK(cudaMallocHost(&h_ovf, sizeof(int))); *h_ovf = 0;
       CUDA_OK(cudaEventCreateWithFlags(&ovf_ev, cudaEventDisableTiming));
       cudaFuncAttributes fl; CUDA_OK(cudaFuncGetAttributes(&fl, step_kernel<Real, DL>));
@@ -324,10 +325,17 @@ struct Batch : BatchBase {
   int step(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc, void* fobs, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
     if (!act || !obs || !rew || !term || !trunc) return set_err("step: null buffer");
+    return step_range(act, obs, rew, term, trunc, fobs, s, 0, n, 0);
+  }
+  // Steps the environments [lo, lo + cnt) (buffers are the whole batch's; `slot` selects the overflow counter, so that
+  // ranges stepped concurrently on different streams do not share one).
+  int step_range(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc, void* fobs, cudaStream_t s, long long lo, long long cnt, int slot) {
     KArgs<Real> a = base; a.op = OP_STEP; a.seed = seed;
-    a.act = (const Real*)act; a.obs = (Real*)obs; a.rew = (Real*)rew; a.term = term; a.trunc = trunc; a.final_obs = (Real*)fobs;
+    a.n = cnt; a.st = d_state + lo; a.env_base = base.env_base + (unsigned long long)lo;
+    a.act = (const Real*)act + lo * act_dim; a.obs = (Real*)obs + lo * obs_dim; a.rew = (Real*)rew + lo; a.term = term + lo; a.trunc = trunc + lo;
+    a.final_obs = fobs ? (Real*)fobs + lo * obs_dim : nullptr;
     constexpr int WF = warps_per_block<Real, D>();
-    const unsigned full_blocks = (unsigned)((n + WF - 1) / WF);
+    const unsigned full_blocks = (unsigned)((cnt + WF - 1) / WF);
     if constexpr (!HAS_LITE) return launch_step<D>(a, s, full_blocks);
     else {
       // Two tiers.  The lite size class (small row / contact caps -> small arena -> more resident warps) steps every
@@ -336,32 +344,33 @@ struct Batch : BatchBase {
       // overflow count is read back asynchronously (one step late), so stepping never synchronises with the host.
       if (ovf_pending && cudaEventQuery(ovf_ev) == cudaSuccess) {
         ovf_pending = false;
-        const long long cnt = *h_ovf;
-        heavy = heavy ? cnt > n / 8 : cnt > n / 4;
+        const long long c = *h_ovf;
+        heavy = heavy ? c > ovf_of / 8 : c > ovf_of / 4;
       }
       if (single_tier) heavy = true;
-      CUDA_OK(cudaMemsetAsync(d_ovf_count, 0, sizeof(int), s));
+      int* const counter = d_ovf_count + slot;
+      CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), s));
       if (heavy) {
-        a.ovf_count = d_ovf_count; a.lite_maxcon = lite_cap_con; a.lite_maxefc = lite_cap_efc;
+        a.ovf_count = counter; a.lite_maxcon = lite_cap_con; a.lite_maxefc = lite_cap_efc;
         if (int rc = launch_step<D>(a, s, full_blocks)) return rc;
         ++full_steps;
       } else {
         constexpr int WL = warps_per_block<Real, DL>();
-        KArgs<Real> l = a; l.ovf_count = d_ovf_count; l.ovf_list = d_ovf_list; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc;
-        unsigned lite_blocks = (unsigned)((n + WL - 1) / WL);
+        KArgs<Real> l = a; l.ovf_count = counter; l.ovf_list = d_ovf_list + lo; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc;
+        unsigned lite_blocks = (unsigned)((cnt + WL - 1) / WL);
 #ifdef UR3E_PERSISTENT
         if (lite_blocks > (unsigned)(UR3E_BLOCKS_PER_SM * sm_count)) lite_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count);
 #endif
         if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
-        a.list_count = d_ovf_count; a.list = d_ovf_list;
+        a.list_count = counter; a.list = d_ovf_list + lo;
         unsigned tail_blocks = (unsigned)(2 * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;
         if (int rc = launch_step<D>(a, s, tail_blocks)) return rc;
         ++lite_steps;
       }
-      if (!ovf_pending) {
-        CUDA_OK(cudaMemcpyAsync(h_ovf, d_ovf_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+      if (!ovf_pending && slot == 0) {
+        CUDA_OK(cudaMemcpyAsync(h_ovf, counter, sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaEventRecord(ovf_ev, s));
-        ovf_pending = true;
+        ovf_pending = true; ovf_of = cnt;
       }
       return 0;
     }
@@ -372,17 +381,29 @@ struct Batch : BatchBase {
     CUDA_OK(cudaMalloc(&d_rew, sizeof(Real) * n)); CUDA_OK(cudaMalloc(&d_term, n)); CUDA_OK(cudaMalloc(&d_trunc, n));
     return 0;
   }
+  // Host-buffer entry point.  The batch is cut into HOST_CHUNKS ranges that alternate between two streams, so that the
+  // action upload and the result download of one range overlap the stepping of the next (pinned host buffers assumed;
+  // pageable ones still work, the copies then serialise).
+  static constexpr int HOST_CHUNKS = 4;
   int step_host(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc) override {
     CUDA_OK(cudaSetDevice(device));
     if (int rc = ensure_staging()) return rc;
-    cudaStream_t s = own_stream;
-    CUDA_OK(cudaMemcpyAsync(d_act, act, sizeof(Real) * n * act_dim, cudaMemcpyHostToDevice, s));
-    if (int rc = step(d_act, d_obs, d_rew, d_term, d_trunc, nullptr, s)) return rc;
-    CUDA_OK(cudaMemcpyAsync(obs, d_obs, sizeof(Real) * n * obs_dim, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(rew, d_rew, sizeof(Real) * n, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(term, d_term, n, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaMemcpyAsync(trunc, d_trunc, n, cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
+    if (!own_stream2) CUDA_OK(cudaStreamCreateWithFlags(&own_stream2, cudaStreamNonBlocking));
+    const int chunks = n >= 4096 * HOST_CHUNKS ? HOST_CHUNKS : 1;
+    const long long per = (n + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; ++c) {
+      const long long lo = c * per, cnt = (lo + per <= n ? per : n - lo);
+      if (cnt <= 0) break;
+      cudaStream_t s = (c & 1) ? own_stream2 : own_stream;
+      CUDA_OK(cudaMemcpyAsync(d_act + lo * act_dim, (const Real*)act + lo * act_dim, sizeof(Real) * cnt * act_dim, cudaMemcpyHostToDevice, s));
+      if (int rc = step_range(d_act, d_obs, d_rew, d_term, d_trunc, nullptr, s, lo, cnt, c)) return rc;
+      CUDA_OK(cudaMemcpyAsync((Real*)obs + lo * obs_dim, d_obs + lo * obs_dim, sizeof(Real) * cnt * obs_dim, cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync((Real*)rew + lo, d_rew + lo, sizeof(Real) * cnt, cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync(term + lo, d_term + lo, cnt, cudaMemcpyDeviceToHost, s));
+      CUDA_OK(cudaMemcpyAsync(trunc + lo, d_trunc + lo, cnt, cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_OK(cudaStreamSynchronize(own_stream));
+    CUDA_OK(cudaStreamSynchronize(own_stream2));
     return 0;
   }
   int get_state(void* qpos, void* qvel, void* ws, cudaStream_t s) override {
