@@ -85,6 +85,13 @@ int ur3e_batch_step_host(ur3e_batch* b, const void* actions_host, void* obs_host
 /* d.qpos / d.qvel / qacc_warmstart reads and MujocoEnv.set_state + mj_forward (checkpointing, per-step re-seeding in parity tests) */
 int ur3e_batch_get_state(ur3e_batch* b, void* qpos_dev, void* qvel_dev, void* qacc_warmstart_dev, void* stream);
 int ur3e_batch_set_state(ur3e_batch* b, const void* qpos_dev, const void* qvel_dev, const void* qacc_warmstart_dev, void* stream);
+/* d.sensor(name).data of main.xml's logging sensors (assets/main.xml:392-408; readers utils/utils.py:201-245 get_jnt_torques /
+ * get_grasp_contact, controller_func.py:191-211): once a buffer [n, UR3E_NSENSOR] of the batch's dtype is attached, every step
+ * writes, from the last mj_step of the step, [0..7) actuatorfrc (shoulder_pan .. wrist_3, fingers), [7] touch right_pad1_contact,
+ * [8] touch left_pad1_contact, [9..12) d.site("tcp").xpos, [12..21) d.site("tcp").xmat (row-major) as get_task_space_state reads
+ * them after mj_step.  NULL detaches (the default: no cost on the step path). */
+#define UR3E_NSENSOR 21
+int ur3e_batch_set_sensor_buffer(ur3e_batch* b, void* sensors_dev);
 /* episode statistics + solver counters since the last reset of the counters: 16 doubles (see UR3E_STAT_*) summed over the batch */
 int ur3e_batch_stats(ur3e_batch* b, double* stats16_dev, int reset_counters, void* stream);
 enum { UR3E_STAT_EPISODES = 0, UR3E_STAT_RETURN, UR3E_STAT_LENGTH, UR3E_STAT_SUCCESS, UR3E_STAT_TERM_REACH, UR3E_STAT_TERM_TOPPLE,

@@ -129,7 +129,7 @@ def load_mjcf(path):
              frictionloss=[], stiffness=[], springref=[], ref=[], solref=[], solimp=[], margin=[])
     G = dict(name=[], type=[], body=[], pos=[], quat=[], size=[], contype=[], conaffinity=[], condim=[],
              priority=[], friction=[], solref=[], solimp=[], solmix=[], margin=[], gap=[])
-    S = dict(name=[], body=[], pos=[], quat=[])
+    S = dict(name=[], body=[], pos=[], quat=[], size=[])
 
     def add_body(elem, parent, childclass):
         bid = len(B["name"])
@@ -198,6 +198,7 @@ def load_mjcf(path):
                 S["body"].append(bid)
                 S["pos"].append(_floats(a.get("pos"), 3, [0, 0, 0]))
                 S["quat"].append(quat_norm(_floats(a.get("quat"), 4, [1, 0, 0, 0])))
+                S["size"].append(_floats(a.get("size"), 3, [0.005, 0.005, 0.005]))
         B["jntnum"].append(nj)
         inert = elem.find("inertial")
         if inert is None and B["name"][bid] in MESH_INERTIA and not geom_mass and parent >= 0:
@@ -324,7 +325,7 @@ def load_mjcf(path):
     m["geom_solimp"] = f64(G["solimp"], (ng, 5)); m["geom_solmix"] = f64(G["solmix"], (ng,))
     m["geom_margin"] = f64(G["margin"], (ng,)); m["geom_gap"] = f64(G["gap"], (ng,))
     ns = m["nsite"]
-    m["site_bodyid"] = i32(S["body"]); m["site_pos"] = f64(S["pos"], (ns, 3)); m["site_quat"] = f64(S["quat"], (ns, 4))
+    m["site_bodyid"] = i32(S["body"]); m["site_pos"] = f64(S["pos"], (ns, 3)); m["site_quat"] = f64(S["quat"], (ns, 4)); m["site_size"] = f64(S["size"], (ns, 3))
 
     # tendons (fixed only)
     ten = dict(name=[], adr=[], num=[], jnt=[], coef=[])

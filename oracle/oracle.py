@@ -176,6 +176,39 @@ class Data:
     def forward(self): lib().o_forward(self.m.ptr, self.ptr)
     def step(self, n=1): lib().o_step_n(self.m.ptr, self.ptr, n)
 
+    def sensors(self):
+        """main.xml's logging sensors after forward()/step(): 7 x actuatorfrc (= actuator_force) and the two touch sensors
+        right_pad1_contact, left_pad1_contact (reference assets/main.xml:392-408; readers utils/utils.py:201-245).
+        Touch (MuJoCo's mjSENS_TOUCH, restated): sum of the normal forces of the contacts that involve the site's body, have a
+        positive normal force, and whose line through the contact point along the contact normal crosses the site's box."""
+        m = self.m
+        out = np.zeros(9)
+        out[:min(m.nu, 7)] = self.arr("actuator_force")[:7]
+        gb = m.py["geom_bodyid"]; sb = m.py["site_bodyid"]; ssz = m.py["site_size"]
+        sx = self.arr("site_xpos").reshape(-1, 3); sm = self.arr("site_xmat").reshape(-1, 3, 3); f = self.arr("efc_force")
+        for k, name in enumerate(("right_pad1_site", "left_pad1_site")):
+            if name not in m.names["site"]:
+                continue
+            j = m.names["site"].index(name)
+            for c in self.contacts():
+                if c.efc_address < 0 or (gb[c.geom1] != sb[j] and gb[c.geom2] != sb[j]):
+                    continue
+                fn = f[c.efc_address]
+                if fn <= 0:
+                    continue
+                o = sm[j].T @ (np.array(c.pos[:]) - sx[j]); d = sm[j].T @ np.array(c.frame[:3])
+                lo, hi = -np.inf, np.inf          # slab test of the (two-sided) line o + t d against the box |x_i| <= size_i
+                for i in range(3):
+                    if abs(d[i]) < 1e-12:
+                        if abs(o[i]) > ssz[j][i]:
+                            lo, hi = 1.0, 0.0
+                    else:
+                        t1, t2 = (-ssz[j][i] - o[i]) / d[i], (ssz[j][i] - o[i]) / d[i]
+                        lo, hi = max(lo, min(t1, t2)), min(hi, max(t1, t2))
+                if lo <= hi:
+                    out[7 + k] += fn
+        return out
+
     def set_state(self, qpos, qvel):
         self.arr("qpos")[:] = qpos; self.arr("qvel")[:] = qvel
 

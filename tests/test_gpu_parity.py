@@ -273,3 +273,41 @@ def test_model_smaller_than_its_size_class_f64(assets, tmp_path):
         o = obs[0].cpu().numpy()
         worst = max(worst, rel(o[:5], d.qpos), rel(o[5:], d.qvel))
     assert worst < 1e-9, worst
+
+
+def test_logging_sensors_f64(assets):
+    """actuatorfrc, the two pad touch sensors and the tcp pose of every step against the oracle (main.xml; the arm sags under zero
+    torque while the gripper closes, so a pad lands on the table and later the fingers meet): SURVEY 8a row a17."""
+    from scipy.spatial.transform import Rotation
+    from ur3e_b200 import utils as U
+    m = O.Model(assets + "/main.xml"); d = O.Data(m)
+    b = make(assets, "main.xml", 2, torch.float64, ctrl_mode=lib.CTRL_RAW, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=7, frame_skip=1, reset_key=1)
+    b.reset(); sens = b.enable_sensors()
+    qp, qv = m.key("down"); d.reset(); d.set_state(qp, qv)
+    u = np.zeros(7); u[6] = 255.0
+    ut = torch.tensor(np.tile(u, (2, 1)), dtype=torch.float64, device="cuda")
+    worst_f = worst_t = worst_p = 0.0; touched = 0
+    for k in range(700):
+        if k % 20 == 0:                     # re-seed both sides from the oracle state (contact-rich: 1e-4 per step)
+            q0, v0 = d.qpos.copy(), d.qvel.copy()
+            d.set_state(q0, v0); d.arr("qacc_warmstart")[:] = 0
+            b.set_state(torch.tensor(np.tile(q0, (2, 1)), device="cuda"), torch.tensor(np.tile(v0, (2, 1)), device="cuda"))
+        d.ctrl[:] = u; d.step(1)
+        b.step(ut)
+        ref = d.sensors(); got = sens[0].cpu().numpy()
+        worst_f = max(worst_f, rel(got[:7], ref[:7], 1e-2))
+        worst_t = max(worst_t, rel(got[7:9], ref[7:9], 1.0))
+        tcp = m.id("site", "tcp")
+        worst_p = max(worst_p, rel(got[9:12], d.site_xpos.reshape(-1, 3)[tcp]), rel(got[12:21], d.site_xmat.reshape(-1, 9)[tcp], 1.0))
+        touched += int(ref[7] > 0.1 or ref[8] > 0.1)
+        if k == 650:
+            ts = U.get_task_space_state(b)[0].cpu().numpy()
+            rv = Rotation.from_matrix(d.site_xmat.reshape(-1, 3, 3)[tcp]).as_rotvec()
+            assert np.abs(ts[3:6] - rv).max() < 1e-6 and ts[6] == float(ref[8] > 0.1)
+            assert bool(U.get_boolean_grasp_contact(b)[0].item()) == bool((ref[8], ref[7]) > (0.1, 0.1))
+            assert np.abs(U.get_joint_space_state(b)[0, :6].cpu().numpy() - d.qpos[:6]).max() < 1e-6
+            assert np.abs(U.get_jnt_torques(b)[0].cpu().numpy() - ref[:7]).max() < 1e-4
+    assert touched > 100, touched           # the scenario does exercise the touch sensors
+    assert worst_f < 1e-4 and worst_t < 1e-4 and worst_p < 1e-6, (worst_f, worst_t, worst_p)
+    assert torch.equal(sens[0], sens[1])
+    b.enable_sensors(False); b.step(ut)     # detached again: stepping no longer writes

@@ -17,6 +17,7 @@ STAT_NAMES = ["episodes", "return_sum", "length_sum", "successes", "term_reach",
               "unstable_resets", "nefc_sum", "ncon_sum", "solver_iter_sum", "substeps", "overflow_steps"]
 MAXCON = 32
 CACHE_SIZE = 54
+NSENSOR = 21
 
 
 class ModelDims(C.Structure):
@@ -32,7 +33,7 @@ class EnvConfig(C.Structure):
 
 EXPORTS = ["ur3e_last_error", "ur3e_model_load", "ur3e_model_destroy", "ur3e_model_info", "ur3e_model_name2id", "ur3e_model_id2name",
            "ur3e_model_array", "ur3e_model_num_warnings", "ur3e_model_warning", "ur3e_batch_create", "ur3e_batch_destroy", "ur3e_batch_reset",
-           "ur3e_batch_step", "ur3e_batch_step_host", "ur3e_batch_get_state", "ur3e_batch_set_state", "ur3e_batch_stats",
+           "ur3e_batch_step", "ur3e_batch_step_host", "ur3e_batch_get_state", "ur3e_batch_set_state", "ur3e_batch_stats", "ur3e_batch_set_sensor_buffer",
            "ur3e_batch_debug_forward", "ur3e_batch_launch_count", "ur3e_batch_kernel_info", "ur3e_batch_state_bytes", "ur3e_batch_tier_info"]
 
 _lib = None
@@ -64,6 +65,7 @@ def load():
     L.ur3e_batch_get_state.argtypes = [vp, vp, vp, vp, vp]
     L.ur3e_batch_set_state.argtypes = [vp, vp, vp, vp, vp]
     L.ur3e_batch_stats.argtypes = [vp, vp, C.c_int, vp]
+    L.ur3e_batch_set_sensor_buffer.argtypes = [vp, vp]
     L.ur3e_batch_debug_forward.argtypes = [vp, i64, dp, dp, dp, dp, C.POINTER(C.c_int32), dp, dp]
     L.ur3e_batch_launch_count.restype = i64; L.ur3e_batch_launch_count.argtypes = [vp]
     L.ur3e_batch_kernel_info.argtypes = [vp] + [C.POINTER(C.c_int32)] * 4

@@ -99,6 +99,13 @@ class SimBatch:
         ws = self._chk(qacc_warmstart, (self.n, self.model.nv)) if qacc_warmstart is not None else None
         _lib.check(self._L.ur3e_batch_set_state(self.ptr, qp, qv, ws, self._stream()), "ur3e_batch_set_state")
 
+    def enable_sensors(self, on=True):
+        """Attach (or detach) the [n, 21] logging output: after every step `self.sensors` holds, from the step's last mj_step,
+        7 x actuatorfrc, the two touch sensors (reference assets/main.xml:392-408) and the tcp site pose; see ur3e_b200/utils.py."""
+        self.sensors = torch.zeros(self.n, _lib.NSENSOR, dtype=self.dtype, device=self.device) if on else None
+        _lib.check(self._L.ur3e_batch_set_sensor_buffer(self.ptr, C.c_void_p(self.sensors.data_ptr()) if on else None), "ur3e_batch_set_sensor_buffer")
+        return self.sensors
+
     def stats(self, reset=True):
         _lib.check(self._L.ur3e_batch_stats(self.ptr, C.c_void_p(self._stats.data_ptr()), int(reset), self._stream()), "ur3e_batch_stats")
         return self._stats

@@ -26,6 +26,7 @@ struct BatchBase {
   virtual int get_state(void* qpos, void* qvel, void* ws, cudaStream_t s) = 0;
   virtual int set_state(const void* qpos, const void* qvel, const void* ws, cudaStream_t s) = 0;
   virtual int stats(double* out, int reset, cudaStream_t s) = 0;
+  virtual int set_sensor_buffer(void* buf) = 0;
   virtual int debug(long long env, double* M, double* bias, double* qacc, double* fc, int32_t* info, double* con, double* cache) = 0;
   int64_t launches = 0;
   virtual void tier_steps(int64_t* lite, int64_t* full) const { *lite = 0; *full = 0; }

@@ -39,6 +39,7 @@ struct KArgs {
   long long n;
   int op;
   const Real* act; Real* obs; Real* rew; uint8_t* term; uint8_t* trunc; Real* final_obs;
+  Real* sens;   // optional [n, NSENSOR] logging-sensor output of every step (null = off, the normal case)
   const uint8_t* mask;
   unsigned long long seed, env_base;
   const Real* qpos_in; const Real* qvel_in; const Real* ws_in;
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
       s.cap_con = (a.cap_con > 0 && a.cap_con < D::MAXCON) ? a.cap_con : D::MAXCON; s.cap_efc = (a.cap_efc > 0 && a.cap_efc < D::MAXEFC) ? a.cap_efc : D::MAXEFC;
     }
     WARP_SYNC();
-    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev);
+    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev, (a.sens && live) ? a.sens + e * NSENSOR : nullptr);
     if (a.ovf_list) {
       // lite tier: this environment needed more rows / contacts than the lite arena holds; leave its stored state
       // untouched and hand it to the full kernel
@@ -194,6 +195,7 @@ struct Batch : BatchBase {
   long long lite_steps = 0, full_steps = 0, ovf_of = 1; bool single_tier = false; int lite_cap_con = DL::MAXCON, lite_cap_efc = DL::MAXEFC;
   void tier_steps(int64_t* lite, int64_t* full) const override { *lite = lite_steps; *full = full_steps; }
   int64_t last_overflow() const override { return h_ovf ? *h_ovf : 0; }
+  void* sens_dev = nullptr;
   DevModel<Real>* d_model = nullptr;
   struct DevConsts { EnvCfg<Real> c; SolverOpts<Real> opt; };
   DevConsts* d_consts = nullptr;
@@ -334,6 +336,7 @@ struct Batch : BatchBase {
     a.n = cnt; a.st = d_state + lo; a.env_base = base.env_base + (unsigned long long)lo;
     a.act = (const Real*)act + lo * act_dim; a.obs = (Real*)obs + lo * obs_dim; a.rew = (Real*)rew + lo; a.term = term + lo; a.trunc = trunc + lo;
     a.final_obs = fobs ? (Real*)fobs + lo * obs_dim : nullptr;
+    a.sens = sens_dev ? (Real*)sens_dev + lo * NSENSOR : nullptr;
     constexpr int WF = warps_per_block<Real, D>();
     const unsigned full_blocks = (unsigned)((cnt + WF - 1) / WF);
     if constexpr (!HAS_LITE) return launch_step<D>(a, s, full_blocks);
@@ -406,6 +409,7 @@ struct Batch : BatchBase {
     CUDA_OK(cudaStreamSynchronize(own_stream2));
     return 0;
   }
+  int set_sensor_buffer(void* buf) override { sens_dev = buf; return 0; }
   int get_state(void* qpos, void* qvel, void* ws, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
     long long tot = n * 64;

@@ -83,6 +83,7 @@ int ur3e_batch_step(ur3e_batch* b, const void* a, void* o, void* r, uint8_t* te,
 int ur3e_batch_step_host(ur3e_batch* b, const void* a, void* o, void* r, uint8_t* te, uint8_t* tr) { GUARD(b); return b->impl->step_host(a, o, r, te, tr); }
 int ur3e_batch_get_state(ur3e_batch* b, void* qp, void* qv, void* ws, void* stream) { GUARD(b); return b->impl->get_state(qp, qv, ws, (cudaStream_t)stream); }
 int ur3e_batch_set_state(ur3e_batch* b, const void* qp, const void* qv, const void* ws, void* stream) { GUARD(b); return b->impl->set_state(qp, qv, ws, (cudaStream_t)stream); }
+int ur3e_batch_set_sensor_buffer(ur3e_batch* b, void* buf) { GUARD(b); return b->impl->set_sensor_buffer(buf); }
 int ur3e_batch_stats(ur3e_batch* b, double* out, int reset, void* stream) { GUARD(b); if (!out) return set_err("null stats buffer"); return b->impl->stats(out, reset, (cudaStream_t)stream); }
 int ur3e_batch_debug_forward(ur3e_batch* b, int64_t env, double* M, double* bias, double* qacc, double* fc, int32_t* info8, double* con, double* cache) {
   GUARD(b); return b->impl->debug(env, M, bias, qacc, fc, info8, con, cache);

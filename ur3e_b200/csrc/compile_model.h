@@ -164,7 +164,7 @@ DevModel<Real> compile_model(const HostModel& h) {
   for (int k = 0; k < MAXSITE; ++k) {
     int sid = h.name2id(OBJ_SITE, tracked_site_names()[k]);
     if (sid < 0) break;   // tracked sites are a prefix: tcp, handle_site, right_pad1_site, left_pad1_site
-    m.site_body[ns] = h.I("site_bodyid")[sid]; cp(m.site_pos[ns], h.D("site_pos"), 3 * sid, 3); cpmat(m.site_mat[ns], h.D("site_quat"), 4 * sid); ++ns;
+    m.site_body[ns] = h.I("site_bodyid")[sid]; cp(m.site_pos[ns], h.D("site_pos"), 3 * sid, 3); cpmat(m.site_mat[ns], h.D("site_quat"), 4 * sid); cp(m.site_size[ns], h.D("site_size"), 3 * sid, 3); ++ns;
   }
   // main.xml has all four; ur3e_2f85.xml lacks handle_site: track tcp only there unless the prefix continues
   m.nsite = ns;

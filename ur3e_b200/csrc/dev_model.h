@@ -71,7 +71,7 @@ struct DevModel {
   Real eq_data[MAXEQ][6], eq_solref[MAXEQ][2], eq_solimp[MAXEQ][5], eq_invw[MAXEQ];
   // tracked sites
   int site_body[MAXSITE];
-  Real site_pos[MAXSITE][3], site_mat[MAXSITE][9];
+  Real site_pos[MAXSITE][3], site_mat[MAXSITE][9], site_size[MAXSITE][3];
   // actuators: force = gain*ctrl + b0 + b1*len + b2*vel ; moment over at most two dofs
   int act_dof[MAXU][2], act_ctrllimited[MAXU], act_forcelimited[MAXU];
   int dof_nact[MAXV], dof_act[MAXV][2]; Real dof_actcoef[MAXV][2];   // transposed transmission: the (at most two) actuators acting on each dof
@@ -99,6 +99,7 @@ struct EnvCfg {
   Real topple_z;           // max(size_x, size_y) of the mug box (gym_utils.py:8-17)
 };
 
+constexpr int NSENSOR = 21;  // logging record: 7 x actuatorfrc, touch right_pad1_contact, touch left_pad1_contact, tcp xpos (3), tcp xmat (9)
 constexpr int CACHE_SIZE = 3 + 9 + 36 + 6;  // tcp_pos, tcp_mat, J_arm (6x6: rows px,py,pz,rx,ry,rz), qfrc_bias[:6]
 
 }  // namespace ur3e

@@ -66,7 +66,8 @@ struct Arena {
   union { Real Mv[D::NV]; Real dinv[D::NV]; };   // M * search (line search) / reciprocal pivots of the shared-memory factorisations (host build, tree LDL)
   Real site_xpos[D::NS][3], site_xmat[1][9] /* tcp only */, site_velp[D::NS][3];
   Real con_pos[D::MAXCON][3], con_dist[D::MAXCON], con_mu[D::MAXCON];
-  union { Real frame[D::MAXCON][9]; Real H[D::MAXCON][6]; } cu;   // contact frames (row assembly) / cone Hessians (solver)
+  struct { Real frame[D::MAXCON][9]; } cu;   // contact frames: normal, two tangents.  The solver keeps each contact's cone Hessian (6 values)
+                                             // in the tangents' storage (frame[c] + 3); the normal survives for the touch sensors
   Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_jv[D::MAXEFC], efc_Dact[D::MAXEFC];
   union {   // geom frames are dead once the contacts exist; the solver's force / residual vectors reuse their storage
     struct { Real efc_force[D::MAXEFC], efc_jar[D::MAXEFC]; };
@@ -220,7 +221,7 @@ template <typename Real> UR3E_HD void mat_mul3(Real* r, const Real* a, const Rea
 //   B. level by level: R_b = R_p L_b, x_b = x_p + R_p t_b   (lane = one entry of R_b or x_b)
 //   C. every body / geom / site in parallel: inertial frame position, joint axis (cdof), geom and site frames
 template <typename Real, typename D>
-UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
+UR3E_HD void kin_frames(const DevModel<Real>& m, Arena<Real, D>& s) {   // stages A and B: xpos, xmat of every body
   auto& kin = s.u.kin;
   WARP_FOR(b, m.nbody) {
     Real* L = kin.lmat[b]; Real* t = kin.lpos[b];
@@ -268,6 +269,11 @@ UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
     }
     WARP_SYNC();
   }
+}
+
+template <typename Real, typename D>
+UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
+  kin_frames(m, s);
   WARP_FOR(i, m.nbody + m.ngeom + m.nsite) {
     if (i < m.nbody) {
       const int b = i;
@@ -977,7 +983,7 @@ UR3E_HD void constraint_update(const DevModel<Real>& m, Arena<Real, D>& s, bool 
       Real mu = s.con_mu[c], f1 = m.pair_friction[p][0], f2 = m.pair_friction[p][1];
       Real U0 = x * mu, U1 = s.efc_jar[r + 1] * f1, U2 = s.efc_jar[r + 2] * f2;
       Real T = Num<Real>::sqrt(U1 * U1 + U2 * U2), N = U0;
-      Real* Hc = s.cu.H[c];
+      Real* Hc = s.cu.frame[c] + 3;
       if (N >= mu * T || (T <= 0 && N >= 0)) {
         for (int j = 0; j < 3; ++j) { s.efc_force[r + j] = 0; s.efc_Dact[r + j] = 0; }
         Hc[0] = -1;   // marker: no cone hessian
@@ -1093,7 +1099,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
           for (int r = r0; r + 2 < r1 + 0 && r + 2 < D::MAXDENSE; r += 3) {
             Real a0 = s.u.efc_J[r][a], a1 = s.u.efc_J[r + 1][a], a2 = s.u.efc_J[r + 2][a];
             Real b0 = s.u.efc_J[r][b], b1 = s.u.efc_J[r + 1][b], b2 = s.u.efc_J[r + 2][b];
-            const Real* Hc = s.cu.H[s.efc_id[r]];
+            const Real* Hc = s.cu.frame[s.efc_id[r]] + 3;
             if (Hc[0] > 0) h += Hc[0] * a0 * b0 + Hc[1] * (a0 * b1 + a1 * b0) + Hc[2] * (a0 * b2 + a2 * b0) + Hc[3] * a1 * b1 + Hc[4] * (a1 * b2 + a2 * b1) + Hc[5] * a2 * b2;
             else h += s.efc_Dact[r] * a0 * b0 + s.efc_Dact[r + 1] * a1 * b1 + s.efc_Dact[r + 2] * a2 * b2;
           }
@@ -1178,6 +1184,57 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
   constraint_update(m, s, false);
   WARP_FOR(d, nv) s.qfrc_constraint[d] = col_dot(m, s, d, s.efc_force);
   IF_LANE0 s.solver_iter = iter;
+  WARP_SYNC();
+}
+
+// ---------------------------------------------------------------- logging sensors (reference assets/main.xml:392-408)
+// out[0..7) = actuatorfrc of the (up to seven) actuators, out[9..21) = tcp site position and orientation matrix,
+// out[7] / out[8] = touch sensors on the tracked sites 2 / 3
+// (right_pad1_site, left_pad1_site; readers utils/utils.py:201-245, controller_func.py:191-211).  Runs right after the solve
+// of a substep, i.e. on the same pre-integration state MuJoCo evaluates its sensors on.  Cold path: only when the caller gave
+// the batch a sensor buffer.  Body frames are recomputed (their storage holds the Newton matrix by now; J is dead); the
+// contact normals are still in place (the cone Hessians only reuse the tangents' storage).
+template <typename Real, typename D>
+UR3E_PHASE void sensors_cold(const DevModel<Real>& m, Arena<Real, D>& s, Real* out) {
+  WARP_FOR(a, 7) out[a] = a < m.nu ? s.act_force[a] : Real(0);
+  WARP_FOR(i, 12) out[9 + i] = m.nsite > 0 ? (i < 3 ? s.site_xpos[0][i] : s.site_xmat[0][i - 3]) : Real(0);   // the tcp is the first tracked site
+  Real touch[2] = {0, 0};
+  if constexpr (D::HAS_CONTACT) {
+    if (m.nsite >= 4) {
+      kin_frames(m, s);
+      WARP_FOR(c, s.ncon) {
+        const int p = s.con_pair[c], b1 = m.geom_body[m.pair_g1[p]], b2 = m.geom_body[m.pair_g2[p]];
+        const Real fn = s.efc_force[s.con_row[c]];
+        for (int k = 0; k < 2; ++k) {
+          const int j = 2 + k, sb = m.site_body[j];
+          if (fn > 0 && (b1 == sb || b2 == sb)) {
+            Real R[9], dlt[3], loc[3];
+            mat_mul3(R, s.fr.k.xmat[sb], m.site_mat[j]);
+            for (int i = 0; i < 3; ++i) dlt[i] = s.con_pos[c][i] - s.site_xpos[j][i];
+            for (int i = 0; i < 3; ++i) loc[i] = R[i] * dlt[0] + R[3 + i] * dlt[1] + R[6 + i] * dlt[2];   // R^T dlt
+            const Real* nrm = s.cu.frame[c];   // contact normal (world)
+            Real dir[3];
+            for (int i = 0; i < 3; ++i) dir[i] = R[i] * nrm[0] + R[3 + i] * nrm[1] + R[6 + i] * nrm[2];
+            const Real* sz = m.site_size[j];
+            // MuJoCo's touch rule: the line through the contact point along the contact normal has to cross the site's box (slab test)
+            Real lo = -Num<Real>::big, hi = Num<Real>::big;
+            bool in = true;
+            for (int i = 0; i < 3; ++i) {
+              if (Num<Real>::abs(dir[i]) < Real(1e-12)) { if (Num<Real>::abs(loc[i]) > sz[i]) in = false; }
+              else {
+                const Real t1 = (-sz[i] - loc[i]) / dir[i], t2 = (sz[i] - loc[i]) / dir[i];
+                lo = rmax(lo, rmin(t1, t2)); hi = rmin(hi, rmax(t1, t2));
+              }
+            }
+            if (lo > hi) in = false;
+            if (in) touch[k] += fn;
+          }
+        }
+      }
+    }
+  }
+  const Real t0 = warp_sum(touch[0]), t1 = warp_sum(touch[1]);
+  IF_LANE0 { out[7] = t0; out[8] = t1; }
   WARP_SYNC();
 }
 
@@ -1307,7 +1364,7 @@ UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
 // returns a warning mask: 1 bad qpos, 2 bad qvel, 4 bad qacc (mj_checkPos/Vel/Acc + autoreset)
 // opt_cold: the same options in addressable (device) memory, for the out-of-line redo path
 template <typename Real, typename D>
-UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, const SolverOpts<Real>& opt_cold) {
+UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, const SolverOpts<Real>& opt_cold, Real* sens = nullptr) {
   int w = 0;
   WARP_FOR(i, m.nq + m.nv) w |= i < m.nq ? is_bad(s.st.qpos[i]) : 2 * is_bad(s.st.qvel[i - m.nq]);
   w = warp_or(w);
@@ -1318,6 +1375,7 @@ UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts
   wa = warp_or(wa);
   if (wa) { reset_data(m, s); forward_cold(m, s, opt_cold, true); w |= wa; }
   WARP_FOR(d, m.nv) s.st.qacc_ws[d] = s.qacc[d];
+  if (sens) sensors_cold(m, s, sens);
   if (UR3E_BARRIERS & 16) BLOCK_SYNC(); else WARP_SYNC();
   euler(m, s);
   return w;

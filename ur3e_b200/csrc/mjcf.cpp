@@ -100,7 +100,7 @@ struct Builder {
   std::vector<std::string> gname; std::vector<int> gtype, gbody, gcontype, gconaff, gcondim, gprio;
   V gpos, gquat, gsize, gfriction, gsolref, gsolimp, gsolmix, gmargin, ggap;
   // site
-  std::vector<std::string> sname; std::vector<int> sbody; V spos, squat;
+  std::vector<std::string> sname; std::vector<int> sbody; V spos, squat, ssize;
 
   static void push(V& dst, const V& src) { dst.insert(dst.end(), src.begin(), src.end()); }
 
@@ -170,6 +170,7 @@ struct Builder {
         sname.push_back(str(a, "name")); sbody.push_back(bid);
         push(spos, floats(a, "pos", 3, {0, 0, 0}));
         V sq = floats(a, "quat", 4, {1, 0, 0, 0}); quat_norm(sq.data()); push(squat, sq);
+        push(ssize, floats(a, "size", 3, {0.005, 0.005, 0.005}));   // MuJoCo's default site size; box sites give three half-sizes
       } else if (ch.tag == "body" || ch.tag == "light" || ch.tag == "camera") {
       } else fail("unsupported element <" + ch.tag + "> in body '" + bname[bid] + "'");
     }
@@ -428,7 +429,7 @@ HostModel load_mjcf(const std::string& path) {
   set_array(m, "geom_conaffinity", B.gconaff, {ng}); set_array(m, "geom_condim", B.gcondim, {ng}); set_array(m, "geom_priority", B.gprio, {ng});
   set_array(m, "geom_friction", B.gfriction, {ng, 3}); set_array(m, "geom_solref", B.gsolref, {ng, 2}); set_array(m, "geom_solimp", B.gsolimp, {ng, 5});
   set_array(m, "geom_solmix", B.gsolmix, {ng}); set_array(m, "geom_margin", B.gmargin, {ng}); set_array(m, "geom_gap", B.ggap, {ng});
-  set_array(m, "site_bodyid", B.sbody, {ns}); set_array(m, "site_pos", B.spos, {ns, 3}); set_array(m, "site_quat", B.squat, {ns, 4});
+  set_array(m, "site_bodyid", B.sbody, {ns}); set_array(m, "site_pos", B.spos, {ns, 3}); set_array(m, "site_quat", B.squat, {ns, 4}); set_array(m, "site_size", B.ssize, {ns, 3});
 
   // tendons (fixed)
   std::vector<std::string> tname; std::vector<int> tadr, tnum, wjnt; V wcoef;
