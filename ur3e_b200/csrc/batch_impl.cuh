@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
       s.cap_con = (a.cap_con > 0 && a.cap_con < D::MAXCON) ? a.cap_con : D::MAXCON; s.cap_efc = (a.cap_efc > 0 && a.cap_efc < D::MAXEFC) ? a.cap_efc : D::MAXEFC;
     }
     WARP_SYNC();
-    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev, (a.sens && live) ? a.sens + e * NSENSOR : nullptr);
+    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev, live ? a.sens : nullptr, e);
     if (a.ovf_list) {
       // lite tier: this environment needed more rows / contacts than the lite arena holds; leave its stored state
       // untouched and hand it to the full kernel

@@ -1364,7 +1364,7 @@ UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
 // returns a warning mask: 1 bad qpos, 2 bad qvel, 4 bad qacc (mj_checkPos/Vel/Acc + autoreset)
 // opt_cold: the same options in addressable (device) memory, for the out-of-line redo path
 template <typename Real, typename D>
-UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, const SolverOpts<Real>& opt_cold, Real* sens = nullptr) {
+UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, const SolverOpts<Real>& opt_cold, Real* sens_base = nullptr, long long env = 0) {
   int w = 0;
   WARP_FOR(i, m.nq + m.nv) w |= i < m.nq ? is_bad(s.st.qpos[i]) : 2 * is_bad(s.st.qvel[i - m.nq]);
   w = warp_or(w);
@@ -1375,7 +1375,7 @@ UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts
   wa = warp_or(wa);
   if (wa) { reset_data(m, s); forward_cold(m, s, opt_cold, true); w |= wa; }
   WARP_FOR(d, m.nv) s.st.qacc_ws[d] = s.qacc[d];
-  if (sens) sensors_cold(m, s, sens);
+  if (sens_base) sensors_cold(m, s, sens_base + env * NSENSOR);
   if (UR3E_BARRIERS & 16) BLOCK_SYNC(); else WARP_SYNC();
   euler(m, s);
   return w;

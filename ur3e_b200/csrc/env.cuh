@@ -289,13 +289,13 @@ UR3E_PHASE void env_reset(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<
 // ---------------------------------------------------------------- one environment step
 template <typename Real, typename D>
 UR3E_HD StepOut<Real> env_step(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const SolverOpts<Real>& opt, const Real* act,
-                               const SolverOpts<Real>& opt_cold, Real* sens = nullptr) {
+                               const SolverOpts<Real>& opt_cold, Real* sens_base = nullptr, long long env = 0) {
   IF_LANE0 { s.overflow = 0; }
   controller(m, c, s, act);
   // per-step counters live in the arena, not in registers: nothing but the loop counter stays live across the substep calls
   IF_LANE0 { s.max_ncon = 0; s.max_nefc = 0; s.sum_ncon = 0; s.sum_nefc = 0; s.sum_iter = 0; s.warn = 0; }
   for (int k = 0; k < c.frame_skip; ++k) {
-    const int w = substep(m, s, opt, opt_cold, k == c.frame_skip - 1 ? sens : nullptr);   // sensors of the step's last mj_step
+    const int w = substep(m, s, opt, opt_cold, k == c.frame_skip - 1 ? sens_base : nullptr, env);   // sensors of the step's last mj_step
     IF_LANE0 {
       s.warn |= w; s.sum_nefc += s.nefc; s.sum_ncon += s.ncon; s.sum_iter += s.solver_iter;
       if (s.ncon > s.max_ncon) s.max_ncon = s.ncon;
