@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
 
 // The step path.  One warp per environment; the block's warps pass the substep phases together (block barriers), so every
 // warp of the block runs the same trip count: a warp without work repeats the last environment and does not store.
-template <typename Real, typename D>
+// SENS: the variant that also writes the logging sensors (a.sens); the normal one carries no trace of that call.
+template <typename Real, typename D, bool SENS = false>
 __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_PER_SM) step_kernel(const KArgs<Real> a) {
   constexpr int WPB = warps_per_block<Real, D>();
   extern __shared__ int4 smem_raw[];
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
       s.cap_con = (a.cap_con > 0 && a.cap_con < D::MAXCON) ? a.cap_con : D::MAXCON; s.cap_efc = (a.cap_efc > 0 && a.cap_efc < D::MAXEFC) ? a.cap_efc : D::MAXEFC;
     }
     WARP_SYNC();
-    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev, live ? a.sens : nullptr, e);
+    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev, (SENS && live) ? a.sens : nullptr, e);
     if (a.ovf_list) {
       // lite tier: this environment needed more rows / contacts than the lite arena holds; leave its stored state
       // untouched and hand it to the full kernel
@@ -295,10 +296,12 @@ struct Batch : BatchBase {
     wpb = WPB; regs = fa.numRegs; arena_bytes = (int)arena_stride<Real, D>(); state_bytes = (int)sizeof(EnvState<Real, D>);
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, env_kernel<Real, D>, WPB * 32, smem));
     CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaDeviceProp prop; CUDA_OK(cudaGetDeviceProperties(&prop, dev)); sm_count = prop.multiProcessorCount;
     if constexpr (HAS_LITE) {
       constexpr int WL = warps_per_block<Real, DL>();
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
+      CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
       CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int) * HOST_CHUNKS)); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
       CUDA_OK(cudaMallocHost(&h_ovf, sizeof(int))); *h_ovf = 0;
       CUDA_OK(cudaEventCreateWithFlags(&ovf_ev, cudaEventDisableTiming));
@@ -319,7 +322,8 @@ struct Batch : BatchBase {
   }
   template <typename DD> int launch_step(KArgs<Real>& a, cudaStream_t s, unsigned blocks) {
     constexpr int W = warps_per_block<Real, DD>();
-    step_kernel<Real, DD><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
+    if (a.sens) step_kernel<Real, DD, true><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
+    else step_kernel<Real, DD><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
     ++launches;
     CUDA_OK(cudaGetLastError());
     return 0;
