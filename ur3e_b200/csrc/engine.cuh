@@ -116,6 +116,11 @@ template <> struct Num<float> {
   static UR3E_HD float cos(float x) { return ::cosf(x); }
   static UR3E_HD float atan2(float y, float x) { return ::atan2f(y, x); }
   static UR3E_HD float pow(float x, float y) { return ::powf(x, y); }
+#if defined(__CUDA_ARCH__)
+  static UR3E_HD float pow_pos(float x, float y) { return x > 0 ? __powf(x, y) : 0.f; }   // x in [0, 1]
+#else
+  static UR3E_HD float pow_pos(float x, float y) { return x > 0 ? ::powf(x, y) : 0.f; }
+#endif
   static UR3E_HD float exp(float x) { return ::expf(x); }
   static UR3E_HD float tanh(float x) { return ::tanhf(x); }
   static UR3E_HD float abs(float x) { return ::fabsf(x); }
@@ -128,6 +133,7 @@ template <> struct Num<double> {
   static UR3E_HD double cos(double x) { return ::cos(x); }
   static UR3E_HD double atan2(double y, double x) { return ::atan2(y, x); }
   static UR3E_HD double pow(double x, double y) { return ::pow(x, y); }
+  static UR3E_HD double pow_pos(double x, double y) { return x > 0 ? ::pow(x, y) : 0.0; }
   static UR3E_HD double exp(double x) { return ::exp(x); }
   static UR3E_HD double tanh(double x) { return ::tanh(x); }
   static UR3E_HD double abs(double x) { return ::fabs(x); }
@@ -193,7 +199,13 @@ template <typename Real> UR3E_HD Real sym_matvec_row(const Real* A, const Real* 
   for (int k = i + 1; k < n; ++k) v += A[k * (k + 1) / 2 + i] * x[k];
   return v;
 }
-template <typename Real> UR3E_PHASE Real sym_matvec_row_cold(const Real* A, const Real* x, int i, int n) { return sym_matvec_row(A, x, i, n); }
+// generic-size fall-back (model smaller than the size class): rolled, inline -- a call here would cost the hot path registers
+template <typename Real> UR3E_HD Real sym_matvec_row_cold(const Real* A, const Real* x, int i, int n) {
+  Real v = 0;
+#pragma unroll 1
+  for (int k = 0; k < n; ++k) v += (k <= i ? A[i * (i + 1) / 2 + k] : A[k * (k + 1) / 2 + i]) * x[k];
+  return v;
+}
 // the same, fully unrolled for the size class (one address select + load + FMA per column, no loop or index arithmetic)
 template <typename Real, int N> UR3E_HD Real sym_matvec_row_n(const Real* A, const Real* x, int i, int n) {
 #if defined(__CUDA_ARCH__)
@@ -434,7 +446,7 @@ template <typename Real> UR3E_HD void make_frame(Real* f) {
 }
 
 template <typename Real>
-UR3E_PHASE int plane_box(const Real* ppos, const Real* pmat, const Real* bpos, const Real* bmat, const Real* size, Real margin, Real* out) {
+UR3E_HD int plane_box(const Real* ppos, const Real* pmat, const Real* bpos, const Real* bmat, const Real* size, Real margin, Real* out) {
   Real n[3] = {pmat[2], pmat[5], pmat[8]};
   Real dif[3] = {bpos[0] - ppos[0], bpos[1] - ppos[1], bpos[2] - ppos[2]};
   Real cd = dot3(dif, n);
@@ -600,10 +612,11 @@ UR3E_HD void jac_col(const DevModel<Real>& m, const Arena<Real, D>& s, int d, co
   } else { out[0] = 0; out[1] = 0; out[2] = 0; }
 }
 
-// general solimp power (never taken by the reference scenes, whose power is 2): out of line so that powf stays off the hot path
-template <typename Real> UR3E_PHASE Real impedance_pow(Real x, Real s3, Real s4) {
-  if (x <= s3) return Num<Real>::pow(x, s4) / Num<Real>::pow(s3, s4 - 1);
-  return 1 - Num<Real>::pow(1 - x, s4) / Num<Real>::pow(1 - s3, s4 - 1);
+// general solimp power (never taken by the reference scenes, whose power is 2): x^p for x in (0, 1) through exp2(p log2 x), a
+// handful of inline instructions in float (powf is ~700 and a call would cost the hot path registers)
+template <typename Real> UR3E_HD Real impedance_pow(Real x, Real s3, Real s4) {
+  if (x <= s3) return Num<Real>::pow_pos(x, s4) / Num<Real>::pow_pos(s3, s4 - 1);
+  return 1 - Num<Real>::pow_pos(1 - x, s4) / Num<Real>::pow_pos(1 - s3, s4 - 1);
 }
 template <typename Real> UR3E_HD Real impedance(const Real* si, Real pos, Real margin) {
   const Real lo = Real(0.0001), hi = Real(0.9999);
@@ -626,7 +639,12 @@ template <typename Real> UR3E_HD void kb_params(const Real* solref, const Real* 
   } else { *K = -solref[0] / rmax(Num<Real>::minval, dmax * dmax); *B = -solref[1] / rmax(Num<Real>::minval, dmax); }
 }
 
-template <typename Real> UR3E_PHASE Real dense_dot_cold(const Real* J, const Real* x, int n) { Real v = 0; for (int k = 0; k < n; ++k) v += J[k] * x[k]; return v; }
+template <typename Real> UR3E_HD Real dense_dot_cold(const Real* J, const Real* x, int n) {
+  Real v = 0;
+#pragma unroll 1
+  for (int k = 0; k < n; ++k) v += J[k] * x[k];
+  return v;
+}
 // J[r] . x for any row (dense rows read the stored Jacobian, sparse rows are one or two entries)
 template <typename Real, typename D>
 UR3E_HD Real row_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int r, const Real* x) {
