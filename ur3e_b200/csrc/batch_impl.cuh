@@ -233,6 +233,7 @@ struct Batch : BatchBase {
     const HostModel hmerged = merge_fixed_bodies(h, bmap);
     if (hmerged.nbody > D::NB) return set_err("merged model has more bodies than the kernel size class");
     DevModel<Real> m = compile_model<Real>(hmerged);
+    if (m.ngeom > D::NG || m.npair > D::NPAIR || m.nv > D::NV || m.nq > D::NQ || m.nu > D::NU) return set_err("model exceeds the kernel size class (geoms / pairs / dofs)");
     if (m.ndeq > 3 * D::MAXCONNECT) return set_err("model has more connect equalities than the kernel size class stores rows for");
     auto body = [&](const char* nm) { int b = h.name2id(OBJ_BODY, nm); return b >= 0 ? bmap[b] : -1; };
     CUDA_OK(cudaMalloc(&d_model, sizeof m)); CUDA_OK(cudaMemcpy(d_model, &m, sizeof m, cudaMemcpyHostToDevice));
@@ -288,6 +289,10 @@ struct Batch : BatchBase {
       CUDA_OK(cudaMalloc(&d_consts, sizeof hc)); CUDA_OK(cudaMemcpy(d_consts, &hc, sizeof hc, cudaMemcpyHostToDevice));
       base.c_dev = &d_consts->c; base.opt_dev = &d_consts->opt; }
     act_dim = c.act_dim; obs_dim = c.obs_dim; single_tier = cfg.single_tier != 0;
+    if constexpr (HAS_LITE && DL::EXACT) {
+      // the lite kernel is compiled for exactly these sizes (Dims::EXACT); any other model of this class runs on the full tier alone
+      if (m.nv != DL::NV || m.nbody != DL::NB || m.nq != DL::NQ || m.nu != DL::NU || m.ngeom != DL::NG || m.npair != DL::NPAIR) single_tier = true;
+    }
     if (cfg.lite_max_contacts > 0 && cfg.lite_max_contacts < DL::MAXCON) lite_cap_con = cfg.lite_max_contacts;
     if (cfg.lite_max_rows > 0 && cfg.lite_max_rows < DL::MAXEFC) lite_cap_efc = cfg.lite_max_rows;
     size_t smem = arena_stride<Real, D>() * WPB;

@@ -11,8 +11,11 @@
 
 namespace ur3e {
 
-template <int NB_, int NV_, int NQ_, int NU_, int NG_, int NPAIR_, int MAXCON_, int MAXEFC_, int SPLIT_ = NV_>
+template <int NB_, int NV_, int NQ_, int NU_, int NG_, int NPAIR_, int MAXCON_, int MAXEFC_, int SPLIT_ = NV_, bool EXACT_ = false>
 struct Dims {
+  // EXACT: the kernel is only ever launched for a model whose sizes equal NB / NV / NQ / NU / NG / NPAIR (checked at batch
+  // creation), so those loop bounds are compile-time constants: WARP_FOR over <= 32 items becomes a predicate, no loop
+  static constexpr bool EXACT = EXACT_;
   // dofs [SPLIT, NV) belong to the model's last kinematic tree (the mug's free joint): M never couples them to the dofs
   // before, and the Newton matrix only does while a constraint spans both (a pad touching the mug) -- see chol_solve_reg_body
   static constexpr int SPLIT = SPLIT_;
@@ -26,8 +29,8 @@ struct Dims {
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // body counts are after fixed-body merging (merge_bodies.h)          // assets/ur3e_raw.xml
 using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 12, 56>;    // assets/ur3e_2f85.xml
-using DimsMain = Dims<19, 20, 21, 7, 7, 13, 24, 96, 14>;   // assets/main.xml
-using DimsMainLite = Dims<19, 20, 21, 7, 7, 13, 8, 44, 14>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
+using DimsMain = Dims<19, 20, 21, 7, 6, 13, 24, 96, 14>;   // assets/main.xml (collidable geoms: four pad boxes, the mug, the table plane)
+using DimsMainLite = Dims<19, 20, 21, 7, 6, 13, 8, 44, 14, true>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 constexpr int STAGE_W = 3 + 4 * STAGE_PTS;
@@ -94,6 +97,14 @@ struct Arena {
     Real efc_J[D::MAXDENSE][D::NV];   // dense rows only
   } u;
 };
+
+// model sizes as seen by a kernel of size class D (see Dims::EXACT)
+template <typename D, typename Real> UR3E_HD int nv_(const DevModel<Real>& m) { if constexpr (D::EXACT) return D::NV; else return m.nv; }
+template <typename D, typename Real> UR3E_HD int nb_(const DevModel<Real>& m) { if constexpr (D::EXACT) return D::NB; else return m.nbody; }
+template <typename D, typename Real> UR3E_HD int nq_(const DevModel<Real>& m) { if constexpr (D::EXACT) return D::NQ; else return m.nq; }
+template <typename D, typename Real> UR3E_HD int nu_(const DevModel<Real>& m) { if constexpr (D::EXACT) return D::NU; else return m.nu; }
+template <typename D, typename Real> UR3E_HD int ng_(const DevModel<Real>& m) { if constexpr (D::EXACT) return D::NG; else return m.ngeom; }
+template <typename D, typename Real> UR3E_HD int np_(const DevModel<Real>& m) { if constexpr (D::EXACT) return D::NPAIR; else return m.npair; }
 
 // ---------------------------------------------------------------- scalar math
 template <typename Real> struct Num;
@@ -235,7 +246,7 @@ template <typename Real> UR3E_HD void mat_mul3(Real* r, const Real* a, const Rea
 template <typename Real, typename D>
 UR3E_HD void kin_frames(const DevModel<Real>& m, Arena<Real, D>& s) {   // stages A and B: xpos, xmat of every body
   auto& kin = s.u.kin;
-  WARP_FOR(b, m.nbody) {
+  WARP_FOR(b, nb_<D>(m)) {
     Real* L = kin.lmat[b]; Real* t = kin.lpos[b];
     const int jk = m.body_jkind[b];
     if (b == 0) {
@@ -286,8 +297,8 @@ UR3E_HD void kin_frames(const DevModel<Real>& m, Arena<Real, D>& s) {   // stage
 template <typename Real, typename D>
 UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
   kin_frames(m, s);
-  WARP_FOR(i, m.nbody + m.ngeom + m.nsite) {
-    if (i < m.nbody) {
+  WARP_FOR(i, nb_<D>(m) + ng_<D>(m) + m.nsite) {
+    if (i < nb_<D>(m)) {
       const int b = i;
       if (b > 0) {
         const Real* R = s.fr.k.xmat[b]; const Real* x = s.xpos[b];
@@ -312,13 +323,13 @@ UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
           }
         }
       }
-    } else if (i < m.nbody + m.ngeom) {
-      const int g = i - m.nbody, b = m.geom_body[g]; Real v[3];
+    } else if (i < nb_<D>(m) + ng_<D>(m)) {
+      const int g = i - nb_<D>(m), b = m.geom_body[g]; Real v[3];
       mat_vec3(v, s.fr.k.xmat[b], m.geom_pos[g]);
       for (int k = 0; k < 3; ++k) s.geom_xpos[g][k] = s.xpos[b][k] + v[k];
       mat_mul3(s.geom_xmat[g], s.fr.k.xmat[b], m.geom_mat[g]);
     } else {
-      const int j = i - m.nbody - m.ngeom, b = m.site_body[j]; Real v[3];
+      const int j = i - nb_<D>(m) - ng_<D>(m), b = m.site_body[j]; Real v[3];
       mat_vec3(v, s.fr.k.xmat[b], m.site_pos[j]);
       for (int k = 0; k < 3; ++k) s.site_xpos[j][k] = s.xpos[b][k] + v[k];
       if (j == 0) mat_mul3(s.site_xmat[0], s.fr.k.xmat[b], m.site_mat[0]);
@@ -330,7 +341,7 @@ UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
 // ---------------------------------------------------------------- CRBA + RNE
 template <typename Real, typename D>
 UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
-  const int nb = m.nbody, nv = m.nv;
+  const int nb = nb_<D>(m), nv = nv_<D>(m);
   auto& y = s.u.dyn;
   // body inertias about the tree reference point + body velocities (sum over the dof chain)
   WARP_FOR(b, nb) {
@@ -412,7 +423,7 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
     }
   }
   // actuator forces
-  WARP_FOR(a, m.nu) {
+  WARP_FOR(a, nu_<D>(m)) {
     Real c = s.ctrl[a];
     if (m.act_ctrllimited[a]) c = rmin(rmax(c, m.act_ctrlrange[a][0]), m.act_ctrlrange[a][1]);
     Real len = 0, vel = 0;
@@ -561,7 +572,7 @@ template <typename Real, typename D>
 UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
   if constexpr (!D::HAS_CONTACT) { s.ncon = 0; return; }
   else {
-    WARP_FOR(p, m.npair) {
+    WARP_FOR(p, np_<D>(m)) {
       int g1 = m.pair_g1[p], g2 = m.pair_g2[p];
       Real margin = m.pair_margin[p];
       int n = 0;
@@ -581,12 +592,12 @@ UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
     }
     WARP_SYNC();
     int total = 0;
-    for (int p = 0; p < m.npair; ++p) { int n = s.stage_n[p]; IF_LANE0 s.stage_off[p] = (uint8_t)total; total += n; }
+    for (int p = 0; p < np_<D>(m); ++p) { int n = s.stage_n[p]; IF_LANE0 s.stage_off[p] = (uint8_t)total; total += n; }
     const int capc = s.cap_con;   // <= D::MAXCON; smaller only when the caller lowers the cap (ur3e_env_config.lite_max_contacts)
     int ncon = total > capc ? capc : total;
     IF_LANE0 { s.ncon = ncon; if (total > capc) s.overflow |= 1; }
     WARP_SYNC();
-    WARP_FOR(i, m.npair * STAGE_PTS) {
+    WARP_FOR(i, np_<D>(m) * STAGE_PTS) {
       int p = i / STAGE_PTS, c = i % STAGE_PTS;
       int o = s.stage_off[p] + c;
       if (c < s.stage_n[p] && o < capc) {
@@ -653,7 +664,7 @@ UR3E_HD Real row_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int r, co
 #if defined(__CUDA_ARCH__)
     // float rows of the full size: five 128-bit loads (16-byte aligned rows of 80 bytes are bank-conflict free across lanes)
     if constexpr (sizeof(Real) == 4 && D::NV % 4 == 0) {
-      if (m.nv == D::NV) {
+      if (nv_<D>(m) == D::NV) {
         const float4* J4 = reinterpret_cast<const float4*>(J);
         float v = 0;
 #pragma unroll
@@ -662,7 +673,7 @@ UR3E_HD Real row_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int r, co
       }
     }
 #endif
-    return dense_dot_cold(J, x, m.nv);
+    return dense_dot_cold(J, x, nv_<D>(m));
   }
   const int t = s.efc_type[r], id = s.efc_id[r];
   if (t == ROW_EQJ) { const int d2 = m.eq_o2[id]; Real v = x[m.eq_o1[id]]; if (d2 >= 0) v -= s.eqj_deriv[id] * x[d2]; return v; }
@@ -690,7 +701,7 @@ UR3E_HD Real col_dot(const DevModel<Real>& m, const Arena<Real, D>& s, int d, co
 
 template <typename Real, typename D>
 UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
-  const int nv = m.nv;
+  const int nv = nv_<D>(m);
   // row budget: dense rows = connect equalities + contacts (3 rows each), sparse rows = joint equalities, friction loss, limits
   const int ndeq = m.ndeq, nej = m.nej;
   const int nf = m.nfl;
@@ -1064,7 +1075,7 @@ template <typename Real> struct SolverOpts { int max_iter; int max_ls; Real tol;
 // one Newton iteration; returns 0 = took a step, 1 = converged before stepping, 2 = took a (negligible) last step
 template <typename Real, typename D>
 UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, const Real scale) {
-  const int nv = m.nv, nefc = s.nefc;
+  const int nv = nv_<D>(m), nefc = s.nefc;
     constraint_update(m, s, true);
     Real gg = 0, gref = 0;
     WARP_FOR(d, nv) {
@@ -1169,7 +1180,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
 
 template <typename Real, typename D>
 UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt) {
-  const int nv = m.nv, nefc = s.nefc;
+  const int nv = nv_<D>(m), nefc = s.nefc;
   if (nefc == 0) {
     // unconstrained: qacc = M^-1 qfrc_smooth
     WARP_FOR(e, nv * (nv + 1) / 2 + nv) { s.fr.n.H[e] = e < nv * (nv + 1) / 2 ? s.M[e] : s.qfrc_smooth[e - nv * (nv + 1) / 2]; }
@@ -1214,7 +1225,7 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
 // contact normals are still in place (the cone Hessians only reuse the tangents' storage).
 template <typename Real, typename D>
 UR3E_PHASE void sensors_cold(const DevModel<Real>& m, Arena<Real, D>& s, Real* out) {
-  WARP_FOR(a, 7) out[a] = a < m.nu ? s.act_force[a] : Real(0);
+  WARP_FOR(a, 7) out[a] = a < nu_<D>(m) ? s.act_force[a] : Real(0);
   WARP_FOR(i, 12) out[9 + i] = m.nsite > 0 ? (i < 3 ? s.site_xpos[0][i] : s.site_xmat[0][i - 3]) : Real(0);   // the tcp is the first tracked site
   Real touch[2] = {0, 0};
   if constexpr (D::HAS_CONTACT) {
@@ -1284,9 +1295,9 @@ UR3E_PHASE void forward_cold(const DevModel<Real>& m, Arena<Real, D>& s, const S
 
 template <typename Real, typename D>
 UR3E_PHASE void reset_data(const DevModel<Real>& m, Arena<Real, D>& s) {
-  WARP_FOR(i, m.nq) s.st.qpos[i] = m.qpos0[i];
-  WARP_FOR(i, m.nv) { s.st.qvel[i] = 0; s.st.qacc_ws[i] = 0; s.qacc[i] = 0; }
-  WARP_FOR(i, m.nu) s.ctrl[i] = 0;
+  WARP_FOR(i, nq_<D>(m)) s.st.qpos[i] = m.qpos0[i];
+  WARP_FOR(i, nv_<D>(m)) { s.st.qvel[i] = 0; s.st.qacc_ws[i] = 0; s.qacc[i] = 0; }
+  WARP_FOR(i, nu_<D>(m)) s.ctrl[i] = 0;
   WARP_SYNC();
 }
 
@@ -1298,7 +1309,7 @@ template <typename Real> UR3E_HD int is_bad(Real x) { return !(Num<Real>::abs(x)
 // A = packed lower triangle (i(i+1)/2 + j) held in the Newton matrix storage; x in shared memory.
 template <typename Real, typename D>
 UR3E_PHASE void tree_ldl_solve(const DevModel<Real>& m, Arena<Real, D>& s, Real* x) {
-  const int nv = m.nv;
+  const int nv = nv_<D>(m);
   Real* A = s.fr.n.H;
 #pragma unroll 1
   for (int k = nv - 1; k > 0; --k) {
@@ -1343,7 +1354,7 @@ UR3E_PHASE void tree_ldl_solve(const DevModel<Real>& m, Arena<Real, D>& s, Real*
 
 template <typename Real, typename D>
 UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
-  const int nv = m.nv; const Real h = m.timestep;
+  const int nv = nv_<D>(m); const Real h = m.timestep;
   Real* qa = s.qacc;
   if (m.has_damping) {
     // (M + h diag(damping)) a = qfrc_smooth + qfrc_constraint   
@@ -1384,15 +1395,15 @@ UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
 template <typename Real, typename D>
 UR3E_HD int substep(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<Real>& opt, const SolverOpts<Real>& opt_cold, Real* sens_base = nullptr, long long env = 0) {
   int w = 0;
-  WARP_FOR(i, m.nq + m.nv) w |= i < m.nq ? is_bad(s.st.qpos[i]) : 2 * is_bad(s.st.qvel[i - m.nq]);
+  WARP_FOR(i, nq_<D>(m) + nv_<D>(m)) w |= i < nq_<D>(m) ? is_bad(s.st.qpos[i]) : 2 * is_bad(s.st.qvel[i - nq_<D>(m)]);
   w = warp_or(w);
   if (w) reset_data(m, s);
   forward(m, s, opt, true, true);
   int wa = 0;
-  WARP_FOR(i, m.nv) wa |= 4 * is_bad(s.qacc[i]);
+  WARP_FOR(i, nv_<D>(m)) wa |= 4 * is_bad(s.qacc[i]);
   wa = warp_or(wa);
   if (wa) { reset_data(m, s); forward_cold(m, s, opt_cold, true); w |= wa; }
-  WARP_FOR(d, m.nv) s.st.qacc_ws[d] = s.qacc[d];
+  WARP_FOR(d, nv_<D>(m)) s.st.qacc_ws[d] = s.qacc[d];
   if (sens_base) sensors_cold(m, s, sens_base + env * NSENSOR);
   if (UR3E_BARRIERS & 16) BLOCK_SYNC(); else WARP_SYNC();
   euler(m, s);

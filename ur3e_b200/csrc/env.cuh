@@ -69,13 +69,13 @@ UR3E_HD void pid_task(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real
     F[r] = c.gains[g] * e[r] - c.gains[g + 3] * v;
   }
   WARP_FOR(k, 6) { Real v = ch[48 + k]; for (int r = 0; r < 6; ++r) v += ch[12 + 6 * r + k] * F[r]; s.ctrl[k] = v; }
-  IF_LANE0 s.ctrl[m.nu - 1] = traj[6] * m.act_ctrlrange[m.nu - 1][1];   // grip_ctrl, controller_func.py:183-186
+  IF_LANE0 s.ctrl[nu_<D>(m) - 1] = traj[6] * m.act_ctrlrange[nu_<D>(m) - 1][1];   // grip_ctrl, controller_func.py:183-186
 }
 
 template <typename Real, typename D>
 UR3E_HD void controller(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const Real* act) {
   switch (c.ctrl_mode) {
-    case CTRL_RAW: { WARP_FOR(a, m.nu) s.ctrl[a] = act[a]; break; }
+    case CTRL_RAW: { WARP_FOR(a, nu_<D>(m)) s.ctrl[a] = act[a]; break; }
     case CTRL_PD_JOINT: {
       // controller_func.py:128-167 with move_j.get_joint_delta (move_j.py:30-38)
       WARP_FOR(i, 6) {
@@ -84,7 +84,7 @@ UR3E_HD void controller(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Re
         Real u = c.gains[i] * (tq - q) + c.gains[6 + i] * -s.st.qvel[i];
         s.ctrl[i] = rmin(rmax(u, m.act_ctrlrange[i][0]), m.act_ctrlrange[i][1]);
       }
-      if (m.nu > 6) { IF_LANE0 s.ctrl[m.nu - 1] = act[6] * m.act_ctrlrange[m.nu - 1][1]; }
+      if (nu_<D>(m) > 6) { IF_LANE0 s.ctrl[nu_<D>(m) - 1] = act[6] * m.act_ctrlrange[nu_<D>(m) - 1][1]; }
       break;
     }
     case CTRL_PID_TASK: { Real traj[7]; for (int k = 0; k < 7; ++k) traj[k] = act[k]; pid_task(m, c, s, traj); break; }
@@ -125,7 +125,7 @@ UR3E_HD void controller(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Re
         }
         s.ctrl[i] = u;
       }
-      if (m.nu > 6) { IF_LANE0 s.ctrl[m.nu - 1] = act[6] * m.act_ctrlrange[m.nu - 1][1]; }
+      if (nu_<D>(m) > 6) { IF_LANE0 s.ctrl[nu_<D>(m) - 1] = act[6] * m.act_ctrlrange[nu_<D>(m) - 1][1]; }
       break;
     }
     default: break;
@@ -159,7 +159,7 @@ UR3E_HD ContactFlags contact_flags(const DevModel<Real>& m, const EnvCfg<Real>& 
 template <typename Real, typename D>
 UR3E_HD void write_obs(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const ContactFlags& cf) {
   if (c.obs_kind == OBS_STATE) {
-    WARP_FOR(i, m.nq + m.nv) { if (i < 32) s.obs[i] = i < m.nq ? s.st.qpos[i] : s.st.qvel[i - m.nq]; }
+    WARP_FOR(i, nq_<D>(m) + nv_<D>(m)) { if (i < 32) s.obs[i] = i < nq_<D>(m) ? s.st.qpos[i] : s.st.qvel[i - nq_<D>(m)]; }
   } else {
     const Real* tcp = s.site_xpos[c.site_tcp]; const Real* mug = s.site_xpos[c.site_mug]; const Real* ghost = s.xpos[c.body_ghost];
     IF_LANE0 {
@@ -269,9 +269,9 @@ UR3E_HD StepOut<Real> reward_done(const DevModel<Real>& m, const EnvCfg<Real>& c
 template <typename Real, typename D>
 UR3E_PHASE void env_reset(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const SolverOpts<Real>& opt, uint64_t seed, uint64_t env_id) {
   int key = c.reset_key;
-  WARP_FOR(i, m.nq) s.st.qpos[i] = key >= 0 ? m.key_qpos[key][i] : m.qpos0[i];
-  WARP_FOR(i, m.nv) { s.st.qvel[i] = key >= 0 ? m.key_qvel[key][i] : Real(0); s.st.qacc_ws[i] = 0; s.qacc[i] = 0; }
-  WARP_FOR(i, m.nu) s.ctrl[i] = 0;
+  WARP_FOR(i, nq_<D>(m)) s.st.qpos[i] = key >= 0 ? m.key_qpos[key][i] : m.qpos0[i];
+  WARP_FOR(i, nv_<D>(m)) { s.st.qvel[i] = key >= 0 ? m.key_qvel[key][i] : Real(0); s.st.qacc_ws[i] = 0; s.qacc[i] = 0; }
+  WARP_FOR(i, nu_<D>(m)) s.ctrl[i] = 0;
   WARP_SYNC();
   if (c.reset_noise != NOISE_NONE && c.body_mug >= 0) {
     uint32_t r[4];
