@@ -98,6 +98,17 @@ struct Arena {
   } u;
 };
 
+// Further model constants of an exact-fit size class (tree depth, nnz of M, friction-loss dofs, equalities, tracked sites):
+// specialised for the class, checked against the loaded model at batch creation like the Dims sizes.
+template <typename D> struct StaticModel { static constexpr int NLEVEL = 0, NM = 0, NFL = 0, NEQ = 0, NSITE = 0, NDEQ = 0, NEJ = 0; static constexpr bool DAMPING = false; };
+template <> struct StaticModel<DimsMainLite> { static constexpr int NLEVEL = 10, NM = 102, NFL = 6, NEQ = 3, NSITE = 4, NDEQ = 6, NEJ = 1; static constexpr bool DAMPING = true; };
+#define UR3E_MODEL_CONST(fn, STATIC, field) \
+  template <typename D, typename Real> UR3E_HD auto fn(const DevModel<Real>& m) { if constexpr (D::EXACT) return StaticModel<D>::STATIC; else return m.field; }
+UR3E_MODEL_CONST(nlevel_, NLEVEL, nlevel) UR3E_MODEL_CONST(nM_, NM, nM) UR3E_MODEL_CONST(nfl_, NFL, nfl) UR3E_MODEL_CONST(neq_, NEQ, neq)
+UR3E_MODEL_CONST(nsite_, NSITE, nsite) UR3E_MODEL_CONST(ndeq_, NDEQ, ndeq) UR3E_MODEL_CONST(nej_, NEJ, nej)
+template <typename D, typename Real> UR3E_HD bool has_damping_(const DevModel<Real>& m) { if constexpr (D::EXACT) return StaticModel<D>::DAMPING; else return m.has_damping != 0; }
+template <typename D, typename Real> UR3E_HD int split_(const DevModel<Real>& m) { if constexpr (D::EXACT) return D::SPLIT; else return m.split; }
+
 // model sizes as seen by a kernel of size class D (see Dims::EXACT)
 template <typename D, typename Real> UR3E_HD int nv_(const DevModel<Real>& m) { if constexpr (D::EXACT) return D::NV; else return m.nv; }
 template <typename D, typename Real> UR3E_HD int nb_(const DevModel<Real>& m) { if constexpr (D::EXACT) return D::NB; else return m.nbody; }
@@ -276,7 +287,7 @@ UR3E_HD void kin_frames(const DevModel<Real>& m, Arena<Real, D>& s) {   // stage
     }
   }
   WARP_SYNC();
-  for (int lev = 1; lev < m.nlevel; ++lev) {
+  for (int lev = 1; lev < nlevel_<D>(m); ++lev) {
     const int b0 = m.lev_start[lev], cnt = m.lev_start[lev + 1] - b0;
     WARP_FOR(i, 12 * cnt) {
       const int slot = i / 12, e = i - 12 * slot, b = m.lev_body[b0 + slot], p = m.body_parent[b];
@@ -297,7 +308,7 @@ UR3E_HD void kin_frames(const DevModel<Real>& m, Arena<Real, D>& s) {   // stage
 template <typename Real, typename D>
 UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
   kin_frames(m, s);
-  WARP_FOR(i, nb_<D>(m) + ng_<D>(m) + m.nsite) {
+  WARP_FOR(i, nb_<D>(m) + ng_<D>(m) + nsite_<D>(m)) {
     if (i < nb_<D>(m)) {
       const int b = i;
       if (b > 0) {
@@ -405,14 +416,14 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
   // M: f_i = crb(body_i) cdof_i (stored over cdof_dot, which is dead) ; M_ij = cdof_j . f_i
   WARP_FOR(i, nv) mul_inert(y.cdof_dot[i], y.cinert[m.dof_body[i]], s.cdof[i]);
   WARP_SYNC();
-  WARP_FOR(e, m.nM) {
+  WARP_FOR(e, nM_<D>(m)) {
     int i = m.M_i[e], j = m.M_j[e];
     Real v = 0; for (int k = 0; k < 6; ++k) v += s.cdof[j][k] * y.cdof_dot[i][k];
     if (i == j) v += m.dof_armature[i];
     s.M[i * (i + 1) / 2 + j] = v;
   }
   // site linear velocities (mj_objectVelocity, world frame) for the observation
-  WARP_FOR(j, m.nsite) {
+  WARP_FOR(j, nsite_<D>(m)) {
     int b = m.site_body[j];
     if (m.body_lastdof[b] < 0) { s.site_velp[j][0] = s.site_velp[j][1] = s.site_velp[j][2] = 0; }
     else {
@@ -703,8 +714,8 @@ template <typename Real, typename D>
 UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nv = nv_<D>(m);
   // row budget: dense rows = connect equalities + contacts (3 rows each), sparse rows = joint equalities, friction loss, limits
-  const int ndeq = m.ndeq, nej = m.nej;
-  const int nf = m.nfl;
+  const int ndeq = ndeq_<D>(m), nej = nej_<D>(m);
+  const int nf = nfl_<D>(m);
   int mlo = 0, mhi = 0;   // bit d: lower / upper limit of dof d is active (dist < margin)
   WARP_FOR(d, nv) {
     if (m.dof_limited[d]) {
@@ -729,12 +740,12 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   if (nefc > cape) { nefc = cape; IF_LANE0 s.overflow |= 2; }
   // row groups: dense rows that share one column set (used by the Hessian assembly)
   int ngrp = 0, coupled = 0;
-  const int lowmask = (int)((1u << m.split) - 1u);
+  const int lowmask = (int)((1u << split_<D>(m)) - 1u);
   auto spans = [lowmask](int mask) { return (mask & lowmask) != 0 && (mask & ~lowmask) != 0; };
-  for (int e = 0; e < m.neq; ++e) if (m.eq_kind[e] != EK_CONNECT && m.eq_o2[e] >= 0) coupled |= spans((1 << m.eq_o1[e]) | (1 << m.eq_o2[e]));
+  for (int e = 0; e < neq_<D>(m); ++e) if (m.eq_kind[e] != EK_CONNECT && m.eq_o2[e] >= 0) coupled |= spans((1 << m.eq_o1[e]) | (1 << m.eq_o2[e]));
   {
     int row = 0;
-    for (int e = 0; e < m.neq; ++e) if (m.eq_kind[e] == EK_CONNECT) {
+    for (int e = 0; e < neq_<D>(m); ++e) if (m.eq_kind[e] == EK_CONNECT) {
       const int mask = (int)(m.body_dofmask[m.eq_o1[e]] | m.body_dofmask[m.eq_o2[e]]);
       IF_LANE0 { s.grp_row0[ngrp] = (uint8_t)row; s.grp_nrow[ngrp] = 3; s.grp_mask[ngrp] = mask; }
       coupled |= spans(mask);
@@ -768,7 +779,7 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
   // rows: efc_aref temporarily holds pos, efc_jv holds margin
   {
     int row = 0, rj = rej0;
-    for (int e = 0; e < m.neq; ++e) {
+    for (int e = 0; e < neq_<D>(m); ++e) {
       if (m.eq_kind[e] == EK_CONNECT) {
         int b1 = m.eq_o1[e], b2 = m.eq_o2[e];
         Real a1[3], a2[3], v[3];
@@ -1094,7 +1105,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
       const int ntri = nv * (nv + 1) / 2;
       WARP_FOR(e, ntri + nv) s.fr.n.H[e] = e < ntri ? s.M[e] : -s.grad[e - ntri];
       WARP_SYNC();
-      WARP_FOR(i, nv + m.neq) {
+      WARP_FOR(i, nv + neq_<D>(m)) {
         if (i < nv) {
           Real h = 0;
           int r = s.sp_fl[i]; if (r != 255) h += s.efc_Dact[r];
@@ -1138,7 +1149,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
       WARP_SYNC();
     }
 #if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
-    chol_solve_reg_body<Real, D::NV, D::SPLIT>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.search, s.coupled != 0 || m.split != D::SPLIT);   // inlined in the Newton loop; the Euler step and the unconstrained case share the out-of-line copy
+    chol_solve_reg_body<Real, D::NV, D::SPLIT>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.search, s.coupled != 0 || split_<D>(m) != D::SPLIT);   // inlined in the Newton loop; the Euler step and the unconstrained case share the out-of-line copy
 #else
     chol_solve_aug(s, nv, s.search);
 #endif
@@ -1187,7 +1198,7 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
     WARP_FOR(d, nv) s.qfrc_constraint[d] = 0;
     WARP_SYNC();
 #if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
-    chol_solve_reg<Real, D::NV, D::SPLIT>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.qacc, m.split != D::SPLIT);   // H = M here
+    chol_solve_reg<Real, D::NV, D::SPLIT>(s.fr.n.H, s.fr.n.H + nv * (nv + 1) / 2, nv, s.qacc, split_<D>(m) != D::SPLIT);   // H = M here
 #else
     chol_solve_aug(s, nv, s.qacc);
 #endif
@@ -1226,10 +1237,10 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
 template <typename Real, typename D>
 UR3E_PHASE void sensors_cold(const DevModel<Real>& m, Arena<Real, D>& s, Real* out) {
   WARP_FOR(a, 7) out[a] = a < nu_<D>(m) ? s.act_force[a] : Real(0);
-  WARP_FOR(i, 12) out[9 + i] = m.nsite > 0 ? (i < 3 ? s.site_xpos[0][i] : s.site_xmat[0][i - 3]) : Real(0);   // the tcp is the first tracked site
+  WARP_FOR(i, 12) out[9 + i] = nsite_<D>(m) > 0 ? (i < 3 ? s.site_xpos[0][i] : s.site_xmat[0][i - 3]) : Real(0);   // the tcp is the first tracked site
   Real touch[2] = {0, 0};
   if constexpr (D::HAS_CONTACT) {
-    if (m.nsite >= 4) {
+    if (nsite_<D>(m) >= 4) {
       kin_frames(m, s);
       WARP_FOR(c, s.ncon) {
         const int p = s.con_pair[c], b1 = m.geom_body[m.pair_g1[p]], b2 = m.geom_body[m.pair_g2[p]];
@@ -1356,13 +1367,13 @@ template <typename Real, typename D>
 UR3E_HD void euler(const DevModel<Real>& m, Arena<Real, D>& s) {
   const int nv = nv_<D>(m); const Real h = m.timestep;
   Real* qa = s.qacc;
-  if (m.has_damping) {
+  if (has_damping_<D>(m)) {
     // (M + h diag(damping)) a = qfrc_smooth + qfrc_constraint   
 #if defined(__CUDA_ARCH__) && UR3E_REG_CHOL
     // M is dead after this step (the next substep rebuilds it), so the damping goes onto its diagonal in place
     WARP_FOR(d, nv) { s.M[d * (d + 1) / 2 + d] += h * m.dof_damping[d]; s.search[d] = s.qfrc_smooth[d] + s.qfrc_constraint[d]; }
     WARP_SYNC();
-    chol_solve_reg<Real, D::NV, D::SPLIT>(s.M, s.search, nv, s.search, m.split != D::SPLIT);   // M + h B never couples two trees
+    chol_solve_reg<Real, D::NV, D::SPLIT>(s.M, s.search, nv, s.search, split_<D>(m) != D::SPLIT);   // M + h B never couples two trees
 #else
     Real* A = s.fr.n.H;
     WARP_FOR(e, nv * (nv + 1) / 2) { const int ab = m.tri_ab[e]; A[e] = s.M[e] + ((ab >> 8) == (ab & 255) ? h * m.dof_damping[ab >> 8] : Real(0)); }
