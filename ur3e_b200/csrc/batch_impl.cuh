@@ -371,15 +371,18 @@ struct Batch : BatchBase {
         ++full_steps;
       } else {
         constexpr int WL = warps_per_block<Real, DL>();
-        KArgs<Real> l = a; l.ovf_count = counter; l.ovf_list = d_ovf_list + lo; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc;
+        KArgs<Real> l = a;
+        if constexpr (DL::MAXCON < D::MAXCON || DL::MAXEFC < D::MAXEFC) { l.ovf_count = counter; l.ovf_list = d_ovf_list + lo; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc; }
         unsigned lite_blocks = (unsigned)((cnt + WL - 1) / WL);
 #ifdef UR3E_PERSISTENT
         if (lite_blocks > (unsigned)(UR3E_BLOCKS_PER_SM * sm_count)) lite_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count);
 #endif
         if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
-        a.list_count = counter; a.list = d_ovf_list + lo;
-        unsigned tail_blocks = (unsigned)(2 * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;
-        if (int rc = launch_step<D>(a, s, tail_blocks)) return rc;
+        if constexpr (DL::MAXCON < D::MAXCON || DL::MAXEFC < D::MAXEFC) {   // an exact-fit twin with the same caps never overflows: no tail
+          a.list_count = counter; a.list = d_ovf_list + lo;
+          unsigned tail_blocks = (unsigned)(2 * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;
+          if (int rc = launch_step<D>(a, s, tail_blocks)) return rc;
+        }
         ++lite_steps;
       }
       if (!ovf_pending && slot == 0) {
