@@ -966,11 +966,19 @@ __device__ __forceinline__ void chol_solve_reg_body(Real* tri, Real* rhs, int n,
   Real* const row = isrow ? tri + lane * (lane + 1) / 2 : rhs;
   const int jmax = isrow ? lane : (isrhs ? n - 1 : -1);   // this lane owns entries 0..jmax of `row`
   Real a[N];
+  if (n == N) {
+    // full-size matrix: plain loads.  Entries beyond a row's diagonal read the neighbouring rows (in bounds) and lanes > N read
+    // the right-hand side: garbage that stays in registers no valid lane ever reads
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    const Real ld = row[j <= jmax ? j : 0];
-    a[j] = j <= jmax ? ld : ((!isrow && j == lane) ? Real(1) : Real(0));
+    for (int j = 0; j < N; ++j) a[j] = row[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const Real ld = row[j <= jmax ? j : 0];
+      a[j] = j <= jmax ? ld : ((!isrow && j == lane) ? Real(1) : Real(0));
+    }
   }
+  const int nstore = isrhs ? jmax + 1 : jmax;   // this lane stores a[k] for k < nstore: the strictly-lower L entries of its row; all of w
   // A = L D L^T with unit L: after step k register a[k] of lane i > k holds L[i][k]; lane N ends with w
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -988,7 +996,7 @@ __device__ __forceinline__ void chol_solve_reg_body(Real* tri, Real* rhs, int n,
 #pragma unroll
       for (int j = k + 1; j < N; ++j) a[j] -= t * __shfl_sync(FULL, a[k], j);
     }
-    if (k < jmax || (isrhs && k == jmax)) row[k] = t;   // strictly-lower L entries, all of w; stored at once, which frees the register
+    if (k < nstore) row[k] = t;   // stored as soon as it is final, which frees the register
   }
   __syncwarp();
   Real xi = lane < n ? rhs[lane] : Real(0);
