@@ -1103,6 +1103,7 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
       Real g = s.Ma[d] - s.qfrc_smooth[d];
       const Real fc = col_dot(m, s, d, s.efc_force);
       g -= fc;
+      s.qfrc_constraint[d] = fc;   // if this pass finds the point converged, these are the final constraint forces
       s.grad[d] = g; gg += g * g; gref += s.Ma[d] * s.Ma[d] + s.qfrc_smooth[d] * s.qfrc_smooth[d] + fc * fc;
     }
     gg = warp_sum(gg); gref = warp_sum(gref);
@@ -1225,14 +1226,18 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
   WARP_SYNC();
   // Newton iterations; each warp runs its own count (the block re-aligns at the barrier that follows the solve: lock-stepping
   // the iterations themselves measured 1.5 % slower once the iteration became cheap, profiles/r1_summary.md)
-  int iter = 0;
+  int iter = 0, rc = 0;
   for (int it = 0; it < opt.max_iter; ++it) {
-    const int rc = newton_iteration(m, s, opt, scale);
+    rc = newton_iteration(m, s, opt, scale);
     if (rc != 1) ++iter;
     if (rc != 0) break;
   }
-  constraint_update(m, s, false);
-  WARP_FOR(d, nv) s.qfrc_constraint[d] = col_dot(m, s, d, s.efc_force);
+  if (rc != 1) {
+    // the last pass moved qacc (negligible step, or the iteration cap): forces at the final point.  After a pass that found the point
+    // converged (rc == 1, the normal exit) efc_force and qfrc_constraint are already those of the final point.
+    constraint_update(m, s, false);
+    WARP_FOR(d, nv) s.qfrc_constraint[d] = col_dot(m, s, d, s.efc_force);
+  }
   IF_LANE0 s.solver_iter = iter;
   WARP_SYNC();
 }
