@@ -148,3 +148,30 @@ def test_two_tier_stepping_f32():
     assert worst_pair < 1e-5, worst_pair         # two-tier == single-tier
     assert worst < 5e-3, worst                   # float32 drift vs the float64 reference episode (tcp / mug / ghost positions)
     assert int(o2[0, 9].item()) == int(g["obs"][T - 1][9])    # same grasp count as the reference at the end
+
+
+def test_f32_production_build_per_step_drift_through_contacts():
+    """float32 production kernels (exact-fit lite tier + full tier) against the float64 build on the fixture's scripted
+    approach-grasp-lift episode, re-seeded from the float64 state before every step: stated per-step bound on the observation
+    (positions 2e-4 m, velocities 2e-2 m/s or rad/s: one step of contact switching at float32 solver tolerances)."""
+    g = np.load(GOLD + "/env_v2.npz")
+    kw = dict(auto_reset=False, reset_noise=lib.NOISE_NONE)
+    e64 = UR3eVecEnv(IDS["v2"], 2, dtype=torch.float64, **kw); e32 = UR3eVecEnv(IDS["v2"], 2, dtype=torch.float32, **kw)
+    e64.reset(); e32.reset()
+    e64.set_state(torch.tensor(np.tile(g["qpos0"], (2, 1)), device="cuda"), torch.tensor(np.tile(g["qvel0"], (2, 1)), device="cuda"))
+    worst_p = worst_v = 0.0; max_ncon = 0.0
+    for k in range(len(g["reward"])):
+        qp, qv, ws = e64.get_state()
+        e32.batch.set_state(qp.float(), qv.float(), ws.float())
+        # set_state refreshes the stale-kinematics cache from the new state on both sides, so both controllers read the same pose
+        e64.batch.set_state(qp, qv, ws)
+        a = torch.tensor(np.tile(g["actions"][k], (2, 1)), device="cuda")
+        o64, r64, t64, _, _ = e64.step(a); o32, r32, t32, _, _ = e32.step(a.float())
+        d = (o32.double() - o64).abs()[0].cpu().numpy()
+        worst_p = max(worst_p, d[:15].max(), d[21:27].max() if d.shape[0] > 27 else d[21:24].max())
+        worst_v = max(worst_v, d[15:21].max())
+        assert bool(t32[0]) == bool(t64[0])
+        st = e32.episode_stats(reset=True)
+        max_ncon = max(max_ncon, st["ncon_sum"] / st["substeps"])
+    assert max_ncon >= 6, max_ncon                # beyond the four mug-table contacts: the pads do press on the mug in this episode
+    assert worst_p < 2e-4 and worst_v < 2e-2, (worst_p, worst_v)
