@@ -15,6 +15,9 @@
 #ifndef UR3E_BLOCKS_PER_SM
 #define UR3E_BLOCKS_PER_SM 2
 #endif
+#ifndef UR3E_LS_TOL
+#define UR3E_LS_TOL 1e-2   // float32 line-search tolerance on |phi'(alpha)| / |phi'(0)|: MuJoCo's default ls_tolerance (1e-5 measured 2-4 % slower, same iteration counts)
+#endif
 #ifndef UR3E_MAX_WPB
 #define UR3E_MAX_WPB 16
 #endif
@@ -281,7 +284,7 @@ struct Batch : BatchBase {
     const bool f64 = sizeof(Real) == 8;
     base.opt.max_iter = cfg.solver_iterations > 0 ? cfg.solver_iterations : (f64 ? 50 : 8);
     base.opt.tol = cfg.solver_tolerance > 0 ? (Real)cfg.solver_tolerance : (f64 ? Real(1e-15) : Real(1e-7));
-    base.opt.max_ls = f64 ? 50 : 12; base.opt.ls_tol = f64 ? Real(1e-14) : Real(1e-5);
+    base.opt.max_ls = f64 ? 50 : 12; base.opt.ls_tol = f64 ? Real(1e-14) : Real(UR3E_LS_TOL);
     base.opt.rtol = f64 ? Real(1e-15) : Real(2e-6);
     base.opt.tol_improve = f64 ? Real(0) : Real(1e-8);   // MuJoCo's default solver tolerance (assets/*.xml do not override it)
     base.m = d_model; base.st = d_state; base.n = n_envs; base.env_base = (unsigned long long)cfg.env_id_base;
