@@ -1174,11 +1174,11 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
     WARP_FOR(d, nv) { g1 += s.search[d] * (s.Ma[d] - s.qfrc_smooth[d]); g2 += s.search[d] * s.Mv[d]; sn += s.search[d] * s.search[d]; pred -= s.search[d] * s.grad[d]; }
     g1 = warp_sum(g1); g2 = warp_sum(g2); sn = warp_sum(sn); pred = Real(0.5) * warp_sum(pred);   // pred = Newton's model decrease of the cost
     // exact line search: safeguarded Newton on phi'(alpha)
-    Real p1, p2, lo = 0, hi = -1, alpha;
-    line_eval(m, s, Real(0), g1, g2, &p1, &p2);
-    if (!(p1 < 0)) return 1;
-    const Real p10 = -p1;
-    alpha = -p1 / p2;
+    // At alpha = 0 nothing has to be evaluated: H is the exact Hessian of the (piecewise quadratic) cost at qacc and H search = -grad,
+    // so phi'(0) = grad . search = -2 pred and phi''(0) = search . H search = 2 pred; the first trial point is the full Newton step.
+    Real p1, p2, lo = 0, hi = -1, alpha = 1;
+    if (!(pred > 0)) return 1;
+    const Real p10 = 2 * pred;
     for (int ls = 0; ls < opt.max_ls; ++ls) {
       line_eval(m, s, alpha, g1, g2, &p1, &p2);
       if (Num<Real>::abs(p1) < opt.ls_tol * p10) break;
