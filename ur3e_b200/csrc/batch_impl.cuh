@@ -410,6 +410,9 @@ struct Batch : BatchBase {
     CUDA_OK(cudaSetDevice(device));
     if (int rc = ensure_staging()) return rc;
     if (!own_stream2) CUDA_OK(cudaStreamCreateWithFlags(&own_stream2, cudaStreamNonBlocking));
+    // this call runs on the batch's own streams: order it after whatever the caller enqueued before (a reset or set_state on its
+    // stream); the call is host-synchronous anyway
+    CUDA_OK(cudaDeviceSynchronize());
     const int chunks = n >= 4096 * HOST_CHUNKS ? HOST_CHUNKS : 1;
     const long long per = (n + chunks - 1) / chunks;
     for (int c = 0; c < chunks; ++c) {
