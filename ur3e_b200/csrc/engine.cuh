@@ -489,8 +489,9 @@ UR3E_HD int plane_box(const Real* ppos, const Real* pmat, const Real* bpos, cons
 }
 
 template <typename Real>
-UR3E_HD int clip_poly(Real* px, Real* py, int n, Real a, Real b, Real c) {
-  Real ox[16], oy[16]; int k = 0;
+UR3E_HD int clip_poly(const Real* px, const Real* py, int n, Real* ox, Real* oy, Real a, Real b, Real c) {
+  // clips (px, py)[0..n) by a x + b y <= c into (ox, oy); the caller ping-pongs two buffers (no copy back)
+  int k = 0;
   for (int i = 0; i < n; ++i) {
     int j = (i + 1 == n) ? 0 : i + 1;
     Real di = a * px[i] + b * py[i] - c, dj = a * px[j] + b * py[j] - c;
@@ -498,7 +499,6 @@ UR3E_HD int clip_poly(Real* px, Real* py, int n, Real a, Real b, Real c) {
     if ((di < 0 && dj > 0) || (di > 0 && dj < 0)) { Real t = di / (di - dj); ox[k] = px[i] + t * (px[j] - px[i]); oy[k] = py[i] + t * (py[j] - py[i]); ++k; }
     if (k >= 15) break;
   }
-  for (int i = 0; i < k; ++i) { px[i] = ox[i]; py[i] = oy[i]; }
   return k;
 }
 
@@ -563,8 +563,9 @@ UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Rea
     px[c] = dot3(r, RA[ru]); py[c] = dot3(r, RA[rv]);
   }
   int n = 4;
-  n = clip_poly(px, py, n, Real(1), Real(0), rs[ru]); n = clip_poly(px, py, n, Real(-1), Real(0), rs[ru]);
-  n = clip_poly(px, py, n, Real(0), Real(1), rs[rv]); n = clip_poly(px, py, n, Real(0), Real(-1), rs[rv]);
+  Real qx[16], qy[16];
+  n = clip_poly(px, py, n, qx, qy, Real(1), Real(0), rs[ru]); n = clip_poly(qx, qy, n, px, py, Real(-1), Real(0), rs[ru]);
+  n = clip_poly(px, py, n, qx, qy, Real(0), Real(1), rs[rv]); n = clip_poly(qx, qy, n, px, py, Real(0), Real(-1), rs[rv]);
   if (n == 0) return 0;
   Real ni[3]; for (int k = 0; k < 3; ++k) ni[k] = isg * IA[ia][k];
   Real nn = dot3(ni, nref);
