@@ -538,7 +538,7 @@ UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Rea
     Real c1[3] = {p1[0], p1[1], p1[2]}, c2[3] = {p2[0], p2[1], p2[2]};
     for (int a = 0; a < 3; ++a) if (a != ei) { Real sg = dot3(A1[a], en) > 0 ? Real(1) : Real(-1); for (int k = 0; k < 3; ++k) c1[k] += sg * s1[a] * A1[a][k]; }
     for (int a = 0; a < 3; ++a) if (a != ej) { Real sg = dot3(A2[a], en) > 0 ? Real(-1) : Real(1); for (int k = 0; k < 3; ++k) c2[k] += sg * s2[a] * A2[a][k]; }
-    const Real* u = A1[ei]; const Real* v = A2[ej];
+    const Real u[3] = {R1[ei], R1[3 + ei], R1[6 + ei]}, v[3] = {R2[ej], R2[3 + ej], R2[6 + ej]};   // axes picked at run time: read from the frames (see below)
     Real w[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
     Real b = dot3(u, v), dd = dot3(u, w), e = dot3(v, w), den = 1 - b * b;
     Real sa = (b * e - dd) / den, sb = (e - b * dd) / den;
@@ -549,30 +549,35 @@ UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Rea
   }
   bool ref1 = code < 3; int ra = ref1 ? code : code - 3;
   const Real *rp = ref1 ? p1 : p2, *ip = ref1 ? p2 : p1, *rs = ref1 ? s1 : s2, *is = ref1 ? s2 : s1;
-  Real(*RA)[3] = ref1 ? A1 : A2; Real(*IA)[3] = ref1 ? A2 : A1;
+  // Axes chosen at run time are read from the frames themselves (axis a of a box = column a of its matrix): indexing the
+  // register copies A1 / A2 dynamically would push them into local memory.
+  const Real* RR = ref1 ? R1 : R2; const Real* IR = ref1 ? R2 : R1;
   Real nref[3]; for (int k = 0; k < 3; ++k) nref[k] = ref1 ? bn[k] : -bn[k];
   int ia = 0; Real mind = Num<Real>::big, isg = 1;
-  for (int a = 0; a < 3; ++a) { Real t = dot3(IA[a], nref); if (-Num<Real>::abs(t) < mind) { mind = -Num<Real>::abs(t); ia = a; isg = t > 0 ? Real(-1) : Real(1); } }
+  for (int a = 0; a < 3; ++a) { Real t = IR[a] * nref[0] + IR[3 + a] * nref[1] + IR[6 + a] * nref[2]; if (-Num<Real>::abs(t) < mind) { mind = -Num<Real>::abs(t); ia = a; isg = t > 0 ? Real(-1) : Real(1); } }
   int iu = (ia + 1) % 3, iv = (ia + 2) % 3, ru = (ra + 1) % 3, rv = (ra + 2) % 3;
+  const Real IAa[3] = {IR[ia], IR[3 + ia], IR[6 + ia]}, IAu[3] = {IR[iu], IR[3 + iu], IR[6 + iu]}, IAv[3] = {IR[iv], IR[3 + iv], IR[6 + iv]};
+  const Real RAu[3] = {RR[ru], RR[3 + ru], RR[6 + ru]}, RAv[3] = {RR[rv], RR[3 + rv], RR[6 + rv]};
+  const Real hia = is[ia], hiu = is[iu], hiv = is[iv];
   Real fc[3], rc[3];
-  for (int k = 0; k < 3; ++k) { fc[k] = ip[k] + isg * is[ia] * IA[ia][k]; rc[k] = rp[k] + rs[ra] * nref[k]; }
+  for (int k = 0; k < 3; ++k) { fc[k] = ip[k] + isg * hia * IAa[k]; rc[k] = rp[k] + rs[ra] * nref[k]; }
   Real px[16], py[16];
   for (int c = 0; c < 4; ++c) {
     Real su = (c == 0 || c == 3) ? Real(1) : Real(-1), sv = (c < 2) ? Real(1) : Real(-1), r[3];
-    for (int k = 0; k < 3; ++k) r[k] = fc[k] + su * is[iu] * IA[iu][k] + sv * is[iv] * IA[iv][k] - rc[k];
-    px[c] = dot3(r, RA[ru]); py[c] = dot3(r, RA[rv]);
+    for (int k = 0; k < 3; ++k) r[k] = fc[k] + su * hiu * IAu[k] + sv * hiv * IAv[k] - rc[k];
+    px[c] = dot3(r, RAu); py[c] = dot3(r, RAv);
   }
   int n = 4;
   Real qx[16], qy[16];
   n = clip_poly(px, py, n, qx, qy, Real(1), Real(0), rs[ru]); n = clip_poly(qx, qy, n, px, py, Real(-1), Real(0), rs[ru]);
   n = clip_poly(px, py, n, qx, qy, Real(0), Real(1), rs[rv]); n = clip_poly(qx, qy, n, px, py, Real(0), Real(-1), rs[rv]);
   if (n == 0) return 0;
-  Real ni[3]; for (int k = 0; k < 3; ++k) ni[k] = isg * IA[ia][k];
+  Real ni[3]; for (int k = 0; k < 3; ++k) ni[k] = isg * IAa[k];
   Real nn = dot3(ni, nref);
   int cnt = 0;
   for (int c = 0; c < n && cnt < STAGE_PTS; ++c) {
     Real base[3], r[3];
-    for (int k = 0; k < 3; ++k) { base[k] = rc[k] + px[c] * RA[ru][k] + py[c] * RA[rv][k]; r[k] = fc[k] - base[k]; }
+    for (int k = 0; k < 3; ++k) { base[k] = rc[k] + px[c] * RAu[k] + py[c] * RAv[k]; r[k] = fc[k] - base[k]; }
     Real h = Num<Real>::abs(nn) > Real(1e-12) ? dot3(ni, r) / nn : Real(0);
     if (h > margin) continue;
     for (int k = 0; k < 3; ++k) { out[3 + 4 * cnt + k] = base[k] + Real(0.5) * h * nref[k]; out[k] = bn[k]; }
