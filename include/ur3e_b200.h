@@ -53,7 +53,7 @@ typedef struct ur3e_env_config {
   double tool_rotvec[3];  /* ur3e_env2.py:74 */
   int64_t env_id_base;    /* global index of env 0 of this batch (multi-GPU sharding: RNG streams are keyed by global id) */
   int32_t single_tier;    /* 1: always step with the full size class (testing aid; default 0 = two-tier stepping where available) */
-  int32_t lite_max_contacts, lite_max_rows;   /* lower the lite tier's caps (0 = built-in 8 contacts / 40 rows); the full tier is unaffected */
+  int32_t lite_max_contacts, lite_max_rows;   /* lower the lite tier's caps (0 = built-in 8 contacts / 44 rows); the full tier is unaffected */
   int32_t reserved_;
 } ur3e_env_config;
 
@@ -104,7 +104,9 @@ int ur3e_batch_debug_forward(ur3e_batch* b, int64_t env, double* M_nvnv, double*
 int64_t ur3e_batch_launch_count(const ur3e_batch* b);
 int ur3e_batch_kernel_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t* warps_per_block, int32_t* blocks_per_sm, int32_t* regs_per_thread);
 /* two-tier stepping of the float32 main.xml batch: out8 = lite arena bytes, lite warps/block, lite blocks/SM,
- * lite registers, lite-tier steps, full-only steps, environments handed to the full tier at the last observed step, 0; all zero when the batch has a single size class */
+ * lite registers, two-tier steps, full-only steps (single_tier), environments the full tier stepped at the last observed step, 0; all zero
+ * when the batch has a single size class.  Which tier steps an environment is decided per environment on the device (its own
+ * recent contact / row counts), so trajectories do not depend on the batch size, the world size or host timing. */
 int ur3e_batch_tier_info(const ur3e_batch* b, int64_t* out8);
 /* bytes of the persistent per-environment record in HBM (read + written once per step) */
 int ur3e_batch_state_bytes(const ur3e_batch* b);

@@ -15,7 +15,8 @@ from ur3e_b200.envs import SB3VecEnv, UR3eVecEnv
 from ur3e_b200.model import Model, asset
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-IDS = {"v2": "gymnasium_env/ur3e-v2", "v0": "gymnasium_env/ur3e-v0", "indirect": "gymnasium_env/imitation_indirect-v0"}
+IDS = {"v2": "gymnasium_env/ur3e-v2", "v0": "gymnasium_env/ur3e-v0", "indirect": "gymnasium_env/imitation_indirect-v0",
+       "direct": "gymnasium_env/imitation_direct-v0"}
 
 
 def rel(a, b, floor=1e-3):
@@ -23,10 +24,12 @@ def rel(a, b, floor=1e-3):
     return float(np.max(np.abs(a - b) / (np.abs(b) + floor)))
 
 
-@pytest.mark.parametrize("kind", ["v2", "v0", "indirect"])
+@pytest.mark.parametrize("kind", ["v2", "v0", "indirect", "direct"])
 def test_env_episode_vs_reference_fixture_f64(kind):
     """A whole scripted approach-grasp-lift episode (260 env-steps, pad-mug contacts) from the fixture's initial state, no
-    re-seeding: float64 build within 1e-4 relative of what the reference's env classes produced."""
+    re-seeding: float64 build within 1e-4 relative of what the reference's env classes produced.  `direct`
+    (imitation_env_direct.py:74-130: raw 7-vector actuator commands, obs 13 with the grasp count and the tcp linear velocity)
+    starts with both pads on the mug and releases half way."""
     g = np.load(GOLD + "/env_%s.npz" % kind)
     env = UR3eVecEnv(IDS[kind], 2, dtype=torch.float64, auto_reset=False, reset_noise=lib.NOISE_NONE)
     env.reset()
@@ -40,6 +43,34 @@ def test_env_episode_vs_reference_fixture_f64(kind):
     assert torch.equal(obs[0], obs[1])                       # identical inputs -> bitwise identical environments
     qpos, qvel, _ = env.get_state()
     assert rel(qpos[0].cpu().numpy(), g["qpos"][-1]) < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["v2", "v0", "indirect", "direct"])
+def test_truncation_step_vs_reference_fixture(kind):
+    """ur3e-v2 increments t before the truncation test (first truncated step 2500), the other three test first
+    (501 / 2501 / 1201).  tests/golden/truncation.npz holds what the reference's own classes reported under a hold-still action;
+    the production float32 kernel, with the shipped max_steps, must truncate on exactly that step (and auto-reset right there)."""
+    first_ref, term_ref = np.load(GOLD + "/truncation.npz")[kind]
+    assert term_ref == 0
+    env = UR3eVecEnv(IDS[kind], 3, dtype=torch.float32, auto_reset=True, reset_noise=lib.NOISE_NONE)
+    obs, _ = env.reset()
+    if kind == "direct":
+        hold = torch.zeros(3, 7, device="cuda")
+        hold[:, :6] = torch.tensor(env.batch.debug_forward(0)["bias_arm"], device="cuda", dtype=torch.float32)    # gravity compensation at the keyframe
+    else:
+        hold = torch.cat([obs[:, :3], torch.zeros(3, 1, device="cuda")], 1).contiguous()
+    first = -1
+    tr_all = []
+    for k in range(1, int(first_ref) + 3):
+        _, _, te, tr, _ = env.step(hold)
+        tr_all.append(tr.clone())
+        assert not te.any()
+    tr_all = torch.stack(tr_all).cpu().numpy()
+    for e in range(3):
+        idx = np.nonzero(tr_all[:, e])[0]
+        assert idx[0] + 1 == first_ref, (kind, idx[:3], first_ref)
+        assert len(idx) == 1                       # auto-reset: t starts again at 0, so no second truncation two steps later
+    assert env.episode_stats()["truncations"] == 3
 
 
 def test_controllers_vs_reference_fixture():

@@ -48,6 +48,34 @@ def test_raw_move_j_f64(assets):
     assert torch.equal(obs[0], obs[1])
 
 
+def test_config1_build_traj_j_stream_f64(assets):
+    """BASELINE.md section 4 gate 1 / SURVEY 8d config 1 on the stated stream: ur3e_raw.xml (dt 1e-4), pd_joint_ctrl through
+    move_j.get_joint_delta with config_j.yml gains, q0 = qvel0 = 0, targets = build_traj_j(zeros(7), hold=120) (np.random.seed(42):
+    500 waypoints x 120 = 60 000 rows, first six columns), no re-seeding: qpos and qvel within 1e-9 relative on every step."""
+    from ur3e_b200.controller import build_traj as BT
+    traj = BT.build_traj_j(np.zeros(7), hold=120)           # [60000, 7]; pinned to the reference's own output by tests/test_build_traj_cpu.py
+    tj = traj.to(torch.float64).cpu().numpy()
+    assert tj.shape == (60000, 7)
+    xml = assets + "/ur3e_raw.xml"
+    loop = OE.OracleCtrlLoop(xml, "pd_joint", OE.GAINS_J)
+    b = make(assets, "ur3e_raw.xml", 1, torch.float64, ctrl_mode=lib.CTRL_PD_JOINT, obs_kind=lib.OBS_STATE, obs_dim=12, act_dim=6, gains=OE.GAINS_J)
+    b.reset()
+    loop.set_state(np.zeros(6), np.zeros(6))
+    acts = traj[:, :6].to(device="cuda", dtype=torch.float64).contiguous()
+    T = tj.shape[0]
+    rec = torch.empty(T, 12, dtype=torch.float64, device="cuda")
+    for k in range(T):
+        obs, *_ = b.step(acts[k:k + 1])
+        rec[k] = obs[0]
+    got = rec.cpu().numpy()
+    worst = 0.0
+    for k in range(T):
+        qp, qv = loop.step(tj[k, :6])
+        worst = max(worst, rel(got[k, :6], qp), rel(got[k, 6:], qv))
+    assert worst < 1e-9, worst
+    assert np.abs(got[:, :6]).max() > 0.3      # the arm does move along the stream
+
+
 def test_gripper_task_space_f64(assets):
     """config 2 semantics: ur3e_2f85.xml, pid_task_ctrl every mj_step, contact-free, 1e-9 relative per step (no re-seeding)."""
     xml = assets + "/ur3e_2f85.xml"
@@ -169,6 +197,49 @@ def test_auto_reset_and_stats(assets):
     st = b.stats_dict()
     assert st["episodes"] == ndone and st["substeps"] == n * 10 * 2
     assert st["length_sum"] == tlen
+
+
+@pytest.mark.parametrize("noise,ylo,yhi", [(lib.NOISE_LOW, -0.1, 0.01), (lib.NOISE_MED, -0.2, 0.1), (lib.NOISE_HIGH, -0.25, 0.2)])
+def test_reset_noise_ranges(assets, noise, ylo, yhi):
+    """gym_utils.py:48-60: mug x in [0, 0.02], y in the level's range, added to keyframe 'down' (main.xml:416-419); both fill their range."""
+    n = 4096
+    b = make(assets, "main.xml", n, torch.float32, ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2,
+             reset_key=1, term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500, reset_noise=noise)
+    o = b.reset(seed=77).double().cpu().numpy()
+    dx, dy = o[:, 3] - 0.29799994, o[:, 4] - 0.13349916
+    assert dx.min() >= -1e-6 and dx.max() <= 0.02 + 1e-6 and dx.max() - dx.min() > 0.95 * 0.02
+    assert dy.min() >= ylo - 1e-6 and dy.max() <= yhi + 1e-6 and dy.max() - dy.min() > 0.95 * (yhi - ylo)
+    assert abs(np.corrcoef(dx, dy)[0, 1]) < 0.1                      # independent draws
+    assert np.abs(o[:, 5] - 0.055111).max() < 1e-6                   # z untouched
+
+
+def test_tier_choice_is_deterministic_and_shard_invariant(assets):
+    """which size class steps an environment is decided per environment on the device, so float32 trajectories are
+    bit-identical between two runs, between one batch of 2 n and two batches of n (world size 1 vs 2, RNG keyed by the global
+    id) and between the device path and the chunked host path -- while a part of the batch is in grasp (full tier)."""
+    n = 96
+    cfg = dict(ctrl_mode=lib.CTRL_PID_TASK_ENV, obs_kind=lib.OBS_V2, obs_dim=24, act_dim=4, gains=OE.GAINS_MUG, frame_skip=2, reset_key=1,
+               term_kind=lib.TERM_V2, reward_kind=lib.REW_V2, max_steps=2500, reset_noise=lib.NOISE_LOW, auto_reset=1, lite_max_contacts=4)
+    whole, again = make(assets, "main.xml", 2 * n, torch.float32, **cfg), make(assets, "main.xml", 2 * n, torch.float32, **cfg)
+    lo, hi = make(assets, "main.xml", n, torch.float32, **cfg), make(assets, "main.xml", n, torch.float32, env_id_base=n, **cfg)
+    o = whole.reset(seed=9).clone(); again.reset(seed=9); lo.reset(seed=9); hi.reset(seed=9)
+    mug0 = o[:, 3:6].clone()
+    full_seen = 0
+    for k in range(260):
+        a = torch.empty(2 * n, 4, device="cuda")
+        a[:, 0:2] = whole.obs[:, 3:5]
+        a[:, 2] = mug0[:, 2] + 0.02 + max(0.0, 0.1 - 0.002 * k)
+        a[:, 3] = 1.0 if k > 90 else 0.0
+        a[::3, 3] = 0.0                                               # a third of the batch never closes: mixed tiers
+        a = a.contiguous()
+        ow = whole.step(a)[0]; oa = again.step(a)[0]
+        ol = lo.step(a[:n].contiguous())[0]; oh = hi.step(a[n:].contiguous())[0]
+        assert torch.equal(ow, oa), k
+        assert torch.equal(ow[:n], ol) and torch.equal(ow[n:], oh), k
+        if k % 20 == 0:
+            torch.cuda.synchronize()
+            full_seen = max(full_seen, whole.kernel_info()["lite"]["last_overflow_envs"])
+    assert 0 < full_seen < 2 * n        # some, not all, environments were stepped by the full tier
 
 
 def test_host_entry_point(assets):

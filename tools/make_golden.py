@@ -32,7 +32,17 @@ def env_episode(cls_name, module, steps, seed, direct=False):
     sink = io.StringIO()
     with contextlib.redirect_stdout(sink):
         env = getattr(mod, cls_name)()
-        obs0, _ = env.reset()
+        if direct:
+            # ImitationEnvDirect.reset_model raises UnboundLocalError in the reference (get_init(..., "stochastic") without a noise_mag,
+            # imitation_env_direct.py:111 vs gym_utils.py:48-60), so the episode starts from the keyframe through MujocoEnv.set_state
+            # through MujocoEnv.set_state -- from a state of the ur3e-v0 fixture in which both pads touch the mug, so that the
+            # observation's grasp count and the tcp velocity are exercised by raw actuator commands
+            v0 = np.load(os.path.join(OUT, "env_v0.npz"))
+            k0 = int(np.argmax(v0["obs"][:, 9] == 2)) + 5
+            env.set_state(v0["qpos"][k0].copy(), v0["qvel"][k0].copy()); env.t = 0
+            obs0 = env._get_obs()
+        else:
+            obs0, _ = env.reset()
     qpos0, qvel0 = env.data.qpos.copy(), env.data.qvel.copy()
     rng = np.random.default_rng(seed)
     rec = dict(qpos0=qpos0, qvel0=qvel0, obs0=np.asarray(obs0, dtype=np.float64), actions=[], obs=[], reward=[], terminated=[], truncated=[], qpos=[], qvel=[],
@@ -41,7 +51,8 @@ def env_episode(cls_name, module, steps, seed, direct=False):
     mug = obs0[3:6].copy()
     for k in range(steps):
         if direct:
-            a = np.zeros(7); a[:6] = rng.uniform(-2, 2, 6); a[6] = 255.0 if k > steps // 2 else 0.0
+            # raw actuator commands: gravity-compensating torques (the controller's stale bias term) plus noise, gripper closed for the first half
+            a = np.zeros(7); a[:6] = env.data.qfrc_bias[:6] + rng.uniform(-1.5, 1.5, 6); a[6] = 255.0 if k < steps // 2 else 0.0
         else:
             # scripted approach, close, lift: exercises pad-mug contacts, grasp flags and the reward branches
             z = mug[2] + 0.02 + max(0.0, 0.1 - 0.002 * k) + (0.0 if k < 170 else 0.0005 * (k - 170))
@@ -53,6 +64,38 @@ def env_episode(cls_name, module, steps, seed, direct=False):
         if te or tr:
             break
     return {k: np.asarray(v) for k, v in rec.items()}
+
+
+def truncation_steps():
+    """Step index (1-based) at which each reference env class first reports truncated=True under a hold-still action:
+    ur3e_env2.py:89-92 increments t before the test (2500), the others test first (ur3e_env.py:183-194 -> 501,
+    imitation_env_indirect.py:97-101 -> 2501, imitation_env_direct.py:99-103 -> 1201).  SURVEY 8a row a15."""
+    out = {}
+    sink = io.StringIO()
+    for name, cls_name, module, direct in (("v2", "UR3eEnv2", "gymnasium_env.envs.ur3e_env2", False), ("v0", "UR3eEnv", "gymnasium_env.envs.ur3e_env", False),
+                                           ("indirect", "ImitationEnvIndirect", "gymnasium_env.envs.imitation_env_indirect", False),
+                                           ("direct", "ImitationEnvDirect", "gymnasium_env.envs.imitation_env_direct", True)):
+        mod = __import__(module, fromlist=[cls_name])
+        np.random.seed(0)
+        with contextlib.redirect_stdout(sink):
+            env = getattr(mod, cls_name)()
+            if not direct:    # ImitationEnvDirect.reset_model raises (see env_episode); the others need it for their error buffers
+                env.reset()
+            qp, qv = gu.get_init(env.model, "deterministic", "down")
+            env.set_state(np.array(qp, dtype=np.float64), np.array(qv, dtype=np.float64)); env.t = 0
+            obs = env._get_obs()
+        hold = np.hstack([obs[:3], 0.0])
+        first, term_any = -1, False
+        for k in range(1, 2600):
+            a = np.hstack([env.data.qfrc_bias[:6], 0.0]) if direct else hold
+            with contextlib.redirect_stdout(sink):
+                o, r, te, tr, _ = env.step(a)
+            term_any |= bool(te)
+            if tr:
+                first = k; break
+        out[name] = np.array([first, int(term_any)], dtype=np.int64)
+        print("truncation", name, "first truncated step", first, "terminated before:", term_any)
+    return out
 
 
 def controller_vectors(seed):
@@ -96,12 +139,20 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     jobs = [("env_v2", "UR3eEnv2", "gymnasium_env.envs.ur3e_env2", 260, 11, False),
             ("env_v0", "UR3eEnv", "gymnasium_env.envs.ur3e_env", 260, 12, False),
-            ("env_indirect", "ImitationEnvIndirect", "gymnasium_env.envs.imitation_env_indirect", 260, 13, False)]
+            ("env_indirect", "ImitationEnvIndirect", "gymnasium_env.envs.imitation_env_indirect", 260, 13, False),
+            ("env_direct", "ImitationEnvDirect", "gymnasium_env.envs.imitation_env_direct", 260, 14, True)]
+    only = sys.argv[1:]
     for name, cls, module, steps, seed, direct in jobs:
+        if only and name not in only:
+            continue
         rec = env_episode(cls, module, steps, seed, direct)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, "steps", len(rec["reward"]), "sum reward %.6f" % rec["reward"].sum(), "grasp max", rec["obs"][:, 23 if rec["obs"].shape[1] == 24 else 9].max(),
               "term", rec["terminated"].any(), "trunc", rec["truncated"].any())
+    if not only or "truncation" in only:
+        np.savez_compressed(os.path.join(OUT, "truncation.npz"), **truncation_steps())
+    if only and "controllers" not in only:
+        return
     cv = controller_vectors(5)
     np.savez_compressed(os.path.join(OUT, "controllers.npz"), **cv)
     print("controllers", cv["u_task"].shape, cv["u_joint"].shape)

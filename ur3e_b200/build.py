@@ -20,8 +20,8 @@ FLAGS += os.environ.get("UR3E_EXTRA_FLAGS", "").split()   # A/B experiments only
 # float32 production units: approximate division / sqrt (2 ulp) and flush-to-zero; sin/cos stay exact. float64 validation units keep IEEE.
 F32_FLAGS = ["-prec-div=false", "-prec-sqrt=false", "-ftz=true"]
 UNITS = ["capi.cu", "mjcf.cpp"] + ["inst_%s_%s.cu" % (r, d) for r in ("f32", "f64") for d in ("raw", "grip", "main")]
-HEADERS = ["batch_base.h", "batch_impl.cuh", "compile_model.h", "dev_model.h", "engine.cuh", "env.cuh", "host_model.h",
-           "warp_model.cuh", "xml_mini.h", os.path.join("..", "..", "include", "ur3e_b200.h")]
+# every header under csrc/ is a dependency of every kernel unit (a missed one would link a stale object silently)
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "ur3e_b200.h")]
 
 
 def _digest(unit):

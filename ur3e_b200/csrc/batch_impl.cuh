@@ -35,9 +35,10 @@ struct KArgs {
   const EnvCfg<Real>* c_dev; const SolverOpts<Real>* opt_dev;
   void* st;   // EnvState<Real, D>[n]; the lite and full size classes of a model share the record layout
   // two-tier stepping (see Batch::step): overflow hand-off from the lite kernel to the full kernel
-  int* ovf_count; int* ovf_list;         // lite tier: environments whose rows / contacts exceeded the lite caps (not stored)
+  int* ovf_count; int* ovf_list;         // lite tier: environments it hands to the full tier (lite caps exceeded, or EnvState::tier > 0); not stored
   const int* list_count; const int* list;  // full tier: process exactly these environments
-  int lite_maxcon, lite_maxefc;          // full kernel used as the only tier: count the environments that would not fit lite
+  int lite_maxcon, lite_maxefc;          // full tier of a two-tier batch: the lite caps, to maintain EnvState::tier
+  int* ovf_stat;                         // full tier: counts the environments whose step did not fit the lite caps (information only)
   int cap_con, cap_efc;                  // row / contact caps of this launch (0 = the size class's own)
   long long n;
   int op;
@@ -82,6 +83,7 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
   IF_LANE0 { s.overflow = 0; s.ncon = 0; s.nefc = 0; s.solver_iter = 0; s.cap_con = D::MAXCON; s.cap_efc = D::MAXEFC; }
   WARP_SYNC();
   const int od = c.obs_dim;
+  if (a.op != OP_DEBUG) { IF_LANE0 s.st.tier = 0; }   // a reset / injected state starts on the lite tier again
   if (a.op == OP_RESET) {
     env_reset(m, c, s, a.opt, a.seed, a.env_base + (unsigned long long)e);
     ContactFlags cf = contact_flags(m, c, s);
@@ -115,9 +117,11 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32) env_kernel(co
   WARP_FOR(i, NW) gst[i] = sst[i];
 }
 
-// The step path.  One warp per environment; the block's warps pass the substep phases together (block barriers), so every
-// warp of the block runs the same trip count: a warp without work repeats the last environment and does not store.
+// The step path.  One warp per environment; the block's warps pass the substep phases together (one block barrier per substep).
+// A warp without work exits: a barrier only waits for the block's non-exited threads, and a warp that has no environment in one
+// pass of the list loop has none in any later pass either (neither has the rest of its block).
 // SENS: the variant that also writes the logging sensors (a.sens); the normal one carries no trace of that call.
+constexpr int TIER_HOLD = 8;   // steps an environment keeps going straight to the full size class after it last needed it
 template <typename Real, typename D, bool SENS = false>
 __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_PER_SM) step_kernel(const KArgs<Real> a) {
   constexpr int WPB = warps_per_block<Real, D>();
@@ -130,14 +134,16 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
   const int od = c.obs_dim;
   long long count = a.n; int iters = 1;
   if (a.list) { count = *a.list_count; const long long per = (long long)gridDim.x * WPB; iters = (int)((count + per - 1) / per); }
-#ifdef UR3E_PERSISTENT
-  else { const long long per = (long long)gridDim.x * WPB; iters = (int)((count + per - 1) / per); }   // A/B: resident grid, strided environments
-#endif
   for (int it = 0; it < iters; ++it) {
     const long long idx = ((long long)it * gridDim.x + blockIdx.x) * WPB + warp;
-    const bool live = idx < count;
-    const long long e = a.list ? (long long)a.list[live ? idx : count - 1] : (live ? idx : count - 1);
-    int4* gst = reinterpret_cast<int4*>(static_cast<EnvState<Real, D>*>(a.st) + e);
+    if (idx >= count) return;
+    const long long e = a.list ? (long long)a.list[idx] : idx;
+    EnvState<Real, D>* const rec = static_cast<EnvState<Real, D>*>(a.st) + e;
+    if (a.ovf_list) {
+      // lite tier: an environment that recently needed the full size class goes straight to it (no wasted lite step)
+      if (rec->tier > 0) { IF_LANE0 { const int k = atomicAdd(a.ovf_count, 1); a.ovf_list[k] = (int)e; } return; }
+    }
+    int4* gst = reinterpret_cast<int4*>(rec);
     int4* sst = reinterpret_cast<int4*>(&s.st);
     WARP_FOR(i, NW) sst[i] = gst[i];
     IF_LANE0 {
@@ -145,22 +151,26 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
       s.cap_con = (a.cap_con > 0 && a.cap_con < D::MAXCON) ? a.cap_con : D::MAXCON; s.cap_efc = (a.cap_efc > 0 && a.cap_efc < D::MAXEFC) ? a.cap_efc : D::MAXEFC;
     }
     WARP_SYNC();
-    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev, (SENS && live) ? a.sens : nullptr, e);
+    StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev, SENS ? a.sens : nullptr, e);
     if (a.ovf_list) {
       // lite tier: this environment needed more rows / contacts than the lite arena holds; leave its stored state
-      // untouched and hand it to the full kernel
-      if (s.overflow) { IF_LANE0 { if (live) { int k = atomicAdd(a.ovf_count, 1); a.ovf_list[k] = (int)e; } } continue; }
-    } else if (a.lite_maxcon > 0 && live) {
-      if (s.max_ncon > a.lite_maxcon || s.max_nefc > a.lite_maxefc) { IF_LANE0 atomicAdd(a.ovf_count, 1); }
+      // untouched and hand it to the full kernel (iters == 1 here, so the warp is done)
+      if (s.overflow) { IF_LANE0 { const int k = atomicAdd(a.ovf_count, 1); a.ovf_list[k] = (int)e; } return; }
+    } else if (a.lite_maxcon > 0) {
+      // full tier of a two-tier batch: keep the environment here while its steps do not fit the lite caps (+ TIER_HOLD steps)
+      IF_LANE0 {
+        const bool big = s.max_ncon > a.lite_maxcon || s.max_nefc > a.lite_maxefc;
+        s.st.tier = big ? TIER_HOLD : (s.st.tier > 0 ? s.st.tier - 1 : 0);
+        if (big && a.ovf_stat) atomicAdd(a.ovf_stat, 1);
+      }
     }
     const int done = r.terminated | r.truncated;
-    if (done && a.final_obs && live) { WARP_FOR(i, od) a.final_obs[e * od + i] = s.obs[i]; }
+    if (done && a.final_obs) { WARP_FOR(i, od) a.final_obs[e * od + i] = s.obs[i]; }
     if (done && c.auto_reset) {
       env_reset(m, *a.c_dev, s, *a.opt_dev, a.seed, a.env_base + (unsigned long long)e);
       ContactFlags cf = contact_flags(m, c, s);
       write_obs(m, c, s, cf);
     }
-    if (!live) continue;
     WARP_FOR(i, od) a.obs[e * od + i] = s.obs[i];
     IF_LANE0 { a.rew[e] = r.reward; a.term[e] = (uint8_t)r.terminated; a.trunc[e] = (uint8_t)r.truncated; }
     WARP_SYNC();
@@ -183,9 +193,8 @@ template <typename Real, typename D>
 __global__ void stats_kernel(EnvState<Real, D>* st, long long n, double* out, int reset) {
   long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (int k = 0; k < NSTAT; ++k) {
-    float v = e < n ? st[e].stat[k] : 0.f;
-    if (reset && e < n) st[e].stat[k] = 0.f;
-    double d = (double)v;
+    double d = 0.0;
+    if (e < n) { d = k == ST_RETURN ? (double)st[e].stat[k].f : (double)st[e].stat[k].i; if (reset) st[e].stat[k].i = 0; }
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
     if ((threadIdx.x & 31) == 0 && d != 0.0) atomicAdd(out + k, d);
   }
@@ -195,10 +204,11 @@ template <typename Real, typename D, typename DL = D>
 struct Batch : BatchBase {
   static constexpr bool HAS_LITE = !std::is_same<D, DL>::value;
   static_assert(sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DL>), "lite and full size classes must share the record layout");
-  int *d_ovf_count = nullptr, *d_ovf_list = nullptr, *h_ovf = nullptr; cudaEvent_t ovf_ev = nullptr; bool ovf_pending = false, heavy = false;
-  long long lite_steps = 0, full_steps = 0, ovf_of = 1; bool single_tier = false; int lite_cap_con = DL::MAXCON, lite_cap_efc = DL::MAXEFC;
+  int *d_ovf_count = nullptr, *d_ovf_list = nullptr, *h_ovf = nullptr; cudaEvent_t ovf_ev = nullptr, order_ev = nullptr; bool ovf_pending = false; int h_ovf_seen = 0;
+  cudaStream_t last_stream = nullptr;   // stream of the latest asynchronous call on this handle (step_host orders itself after it)
+  long long lite_steps = 0, full_steps = 0; bool single_tier = false; int lite_cap_con = DL::MAXCON, lite_cap_efc = DL::MAXEFC;
   void tier_steps(int64_t* lite, int64_t* full) const override { *lite = lite_steps; *full = full_steps; }
-  int64_t last_overflow() const override { return h_ovf ? *h_ovf : 0; }
+  int64_t last_overflow() const override { return (ovf_pending && cudaEventQuery(ovf_ev) != cudaSuccess) ? h_ovf_seen : (h_ovf ? *h_ovf : 0); }
   void* sens_dev = nullptr;
   DevModel<Real>* d_model = nullptr;
   struct DevConsts { EnvCfg<Real> c; SolverOpts<Real> opt; };
@@ -215,7 +225,7 @@ struct Batch : BatchBase {
 
   ~Batch() override {
     cudaSetDevice(device);
-    cudaFree(d_ovf_count); cudaFree(d_ovf_list); if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev);
+    cudaFree(d_ovf_count); cudaFree(d_ovf_list); if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev); if (order_ev) cudaEventDestroy(order_ev);
     cudaFree(d_model); cudaFree(d_consts); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
     if (own_stream) cudaStreamDestroy(own_stream);
     if (own_stream2) cudaStreamDestroy(own_stream2);
@@ -279,7 +289,7 @@ struct Batch : BatchBase {
     if (c.obs_dim != want_obs || c.obs_dim > 32) return set_err("obs_dim does not match obs_kind (expected " + std::to_string(want_obs) + ")");
     int want_act = c.ctrl_mode == CTRL_RAW ? h.nu : c.ctrl_mode == CTRL_PD_JOINT ? (h.nu > 6 ? 7 : 6) : (c.ctrl_mode == CTRL_PID_TASK || c.ctrl_mode == CTRL_PINV) ? 7 : 4;
     if (c.act_dim != want_act) return set_err("act_dim does not match ctrl_mode (expected " + std::to_string(want_act) + ")");
-    if (c.frame_skip < 1) return set_err("frame_skip must be >= 1");
+    if (c.frame_skip < 1 || c.frame_skip > MAX_FRAME_SKIP) return set_err("frame_skip must be in [1, " + std::to_string(MAX_FRAME_SKIP) + "]");
     if (c.reset_key >= h.nkey) return set_err("reset_key out of range");
     const bool f64 = sizeof(Real) == 8;
     base.opt.max_iter = cfg.solver_iterations > 0 ? cfg.solver_iterations : (f64 ? 50 : 8);
@@ -313,7 +323,7 @@ struct Batch : BatchBase {
       constexpr int WL = warps_per_block<Real, DL>();
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
-      CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int) * HOST_CHUNKS)); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
+      CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int) * 2 * HOST_CHUNKS)); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
       CUDA_OK(cudaMallocHost(&h_ovf, sizeof(int))); *h_ovf = 0;
       CUDA_OK(cudaEventCreateWithFlags(&ovf_ev, cudaEventDisableTiming));
       cudaFuncAttributes fl; CUDA_OK(cudaFuncGetAttributes(&fl, step_kernel<Real, DL>));
@@ -327,7 +337,7 @@ struct Batch : BatchBase {
   }
   int reset(const uint8_t* mask, uint64_t sd, void* obs, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
-    seed = sd;
+    seed = sd; last_stream = s;
     KArgs<Real> a = base; a.op = OP_RESET; a.mask = mask; a.seed = sd; a.obs = (Real*)obs;
     return launch(a, s, n);
   }
@@ -342,6 +352,7 @@ struct Batch : BatchBase {
   int step(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc, void* fobs, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
     if (!act || !obs || !rew || !term || !trunc) return set_err("step: null buffer");
+    last_stream = s;
     return step_range(act, obs, rew, term, trunc, fobs, s, 0, n, 0);
   }
   // Steps the environments [lo, lo + cnt) (buffers are the whole batch's; `slot` selects the overflow counter, so that
@@ -356,43 +367,42 @@ struct Batch : BatchBase {
     const unsigned full_blocks = (unsigned)((cnt + WF - 1) / WF);
     if constexpr (!HAS_LITE) return launch_step<D>(a, s, full_blocks);
     else {
-      // Two tiers.  The lite size class (small row / contact caps -> small arena -> more resident warps) steps every
-      // environment; the few that exceed its caps are left untouched and re-stepped by the full size class from a device-side
-      // list.  When more than a quarter of the batch overflows (e.g. a whole batch in grasp) the full class runs alone.  The
-      // overflow count is read back asynchronously (one step late), so stepping never synchronises with the host.
-      if (ovf_pending && cudaEventQuery(ovf_ev) == cudaSuccess) {
-        ovf_pending = false;
-        const long long c = *h_ovf;
-        heavy = heavy ? c > ovf_of / 8 : c > ovf_of / 4;
-      }
-      if (single_tier) heavy = true;
+      // Two tiers.  The lite size class (small row / contact caps -> small arena -> more resident warps) steps every environment
+      // except those whose record says they recently needed the full size class (EnvState::tier); these, and the few that turn
+      // out to exceed the lite caps during the step (left untouched by the lite kernel), are appended to a device-side list that
+      // the full size class then steps from a resident grid.  The choice is a function of each environment's own history, made on
+      // the device: no host read-back, no dependence on the batch size, the chunking of step_host, the world size or timing.
       int* const counter = d_ovf_count + slot;
-      CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), s));
-      if (heavy) {
-        a.ovf_count = counter; a.lite_maxcon = lite_cap_con; a.lite_maxefc = lite_cap_efc;
+      a.lite_maxcon = lite_cap_con; a.lite_maxefc = lite_cap_efc; a.ovf_stat = d_ovf_count + HOST_CHUNKS + slot;
+      if (single_tier) {   // testing aid: the full size class alone, every environment
+        a.lite_maxcon = 0;
         if (int rc = launch_step<D>(a, s, full_blocks)) return rc;
         ++full_steps;
-      } else {
-        constexpr int WL = warps_per_block<Real, DL>();
-        KArgs<Real> l = a;
-        if constexpr (DL::MAXCON < D::MAXCON || DL::MAXEFC < D::MAXEFC) { l.ovf_count = counter; l.ovf_list = d_ovf_list + lo; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc; }
-        unsigned lite_blocks = (unsigned)((cnt + WL - 1) / WL);
-#ifdef UR3E_PERSISTENT
-        if (lite_blocks > (unsigned)(UR3E_BLOCKS_PER_SM * sm_count)) lite_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count);
-#endif
-        if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
-        if constexpr (DL::MAXCON < D::MAXCON || DL::MAXEFC < D::MAXEFC) {   // an exact-fit twin with the same caps never overflows: no tail
-          a.list_count = counter; a.list = d_ovf_list + lo;
-          unsigned tail_blocks = (unsigned)(2 * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;
-          if (int rc = launch_step<D>(a, s, tail_blocks)) return rc;
-        }
-        ++lite_steps;
+        return 0;
       }
-      if (!ovf_pending && slot == 0) {
+      constexpr int WL = warps_per_block<Real, DL>();
+      constexpr bool CAN_OVERFLOW = DL::MAXCON < D::MAXCON || DL::MAXEFC < D::MAXEFC;   // an exact-fit twin with the same caps never overflows: no list, no tail
+      const unsigned lite_blocks = (unsigned)((cnt + WL - 1) / WL);
+      if constexpr (!CAN_OVERFLOW) {
+        KArgs<Real> l = a; l.lite_maxcon = 0; l.ovf_stat = nullptr;
+        if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
+        ++lite_steps;
+        return 0;
+      }
+      CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), s));
+      CUDA_OK(cudaMemsetAsync(a.ovf_stat, 0, sizeof(int), s));
+      KArgs<Real> l = a;
+      l.ovf_count = counter; l.ovf_list = d_ovf_list + lo; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc; l.lite_maxcon = 0; l.ovf_stat = nullptr;
+      if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
+      a.list_count = counter; a.list = d_ovf_list + lo;
+      unsigned tail_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;
+      if (int rc = launch_step<D>(a, s, tail_blocks)) return rc;
+      ++lite_steps;
+      if (!ovf_pending && slot == 0) {   // information only (ur3e_batch_tier_info): size of the full tier's list, read back without synchronising
         CUDA_OK(cudaMemcpyAsync(h_ovf, counter, sizeof(int), cudaMemcpyDeviceToHost, s));
         CUDA_OK(cudaEventRecord(ovf_ev, s));
-        ovf_pending = true; ovf_of = cnt;
-      }
+        ovf_pending = true;
+      } else if (ovf_pending && cudaEventQuery(ovf_ev) == cudaSuccess) { ovf_pending = false; h_ovf_seen = *h_ovf; }
       return 0;
     }
   }
@@ -410,9 +420,12 @@ struct Batch : BatchBase {
     CUDA_OK(cudaSetDevice(device));
     if (int rc = ensure_staging()) return rc;
     if (!own_stream2) CUDA_OK(cudaStreamCreateWithFlags(&own_stream2, cudaStreamNonBlocking));
-    // this call runs on the batch's own streams: order it after whatever the caller enqueued before (a reset or set_state on its
-    // stream); the call is host-synchronous anyway
-    CUDA_OK(cudaDeviceSynchronize());
+    // this call runs on the batch's own streams: order it after the latest asynchronous call on this handle (a reset, step or
+    // set_state on the caller's stream) with an event, so that no other stream of the device is stalled (a trainer's forward pass)
+    if (!order_ev) CUDA_OK(cudaEventCreateWithFlags(&order_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventRecord(order_ev, last_stream));
+    CUDA_OK(cudaStreamWaitEvent(own_stream, order_ev, 0));
+    CUDA_OK(cudaStreamWaitEvent(own_stream2, order_ev, 0));
     const int chunks = n >= 4096 * HOST_CHUNKS ? HOST_CHUNKS : 1;
     const long long per = (n + chunks - 1) / chunks;
     for (int c = 0; c < chunks; ++c) {
@@ -433,6 +446,7 @@ struct Batch : BatchBase {
   int set_sensor_buffer(void* buf) override { sens_dev = buf; return 0; }
   int get_state(void* qpos, void* qvel, void* ws, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
+    last_stream = s;
     long long tot = n * 64;
     state_io_kernel<Real, D><<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(d_state, n, hm.nq, hm.nv, (Real*)qpos, (Real*)qvel, (Real*)ws);
     ++launches;
@@ -442,11 +456,13 @@ struct Batch : BatchBase {
   int set_state(const void* qpos, const void* qvel, const void* ws, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
     if (!qpos || !qvel) return set_err("set_state: null buffer");
+    last_stream = s;
     KArgs<Real> a = base; a.op = OP_SET_STATE; a.qpos_in = (const Real*)qpos; a.qvel_in = (const Real*)qvel; a.ws_in = (const Real*)ws;
     return launch(a, s, n);
   }
   int stats(double* out, int rst, cudaStream_t s) override {
     CUDA_OK(cudaSetDevice(device));
+    last_stream = s;
     CUDA_OK(cudaMemsetAsync(out, 0, 16 * sizeof(double), s));
     stats_kernel<Real, D><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_state, n, out, rst);
     ++launches;

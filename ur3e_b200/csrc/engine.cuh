@@ -43,6 +43,7 @@ enum RowType { ROW_EQ = 0, ROW_EQJ = 1, ROW_FRICTION = 2, ROW_LIMIT_LO = 3, ROW_
 // Persistent per-environment record (lives in HBM between launches, one contiguous 16-byte aligned block per
 // environment so that a warp loads/stores it with coalesced 128-bit accesses).
 constexpr int NSTAT = 14;
+constexpr int MAX_FRAME_SKIP = 256;   // 256 substeps x 112 rows < 2^15: the per-step row / contact / iteration sums are 16-bit
 enum StatSlot { ST_EPISODES = 0, ST_RETURN, ST_LENGTH, ST_SUCCESS, ST_TERM_REACH, ST_TERM_TOPPLE, ST_TERM_COLLISION, ST_TRUNC, ST_UNSTABLE,
                 ST_NEFC, ST_NCON, ST_ITER, ST_SUBSTEPS, ST_OVERFLOW };
 template <typename Real, typename D>
@@ -50,8 +51,11 @@ struct alignas(16) EnvState {
   Real qpos[D::NQ], qvel[D::NV], qacc_ws[D::NV];
   Real cache[CACHE_SIZE];   // stale-kinematics cache read by the next step's controller
   Real ep_return;
-  float stat[NSTAT];        // counters since the last ur3e_batch_stats(reset)
+  union { int i; float f; } stat[NSTAT];   // counters since the last ur3e_batch_stats(reset): 32-bit integers (exact), except ST_RETURN (a float sum)
   int t, episode;
+  int tier;   // two-tier stepping: > 0 = steps this environment still goes straight to the full size class (set by the full tier when a
+              // step needed more contacts / rows than the lite caps; counts down otherwise).  A function of the environment's own history
+              // only, so which kernel steps an environment never depends on the batch size, the chunking or the host's timing.
 };
 
 template <typename Real, typename D>
@@ -89,7 +93,7 @@ struct Arena {
   int lim_lo, lim_hi;
   short nd, rf0, rl0;   // dense rows [0, nd); friction rows from rf0, limit rows from rl0
   short ncon, nefc, ne, nf, nl, ngrp, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
-  short sum_ncon, sum_nefc, sum_iter, warn;   // accumulated over the substeps of one env step
+  short sum_ncon, sum_nefc, sum_iter, warn;   // accumulated over the substeps of one env step (frame_skip <= MAX_FRAME_SKIP keeps them in range)
   short coupled;   // some constraint of this substep has entries on both sides of Dims::SPLIT
   union alignas(16) {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer

@@ -304,21 +304,21 @@ UR3E_HD StepOut<Real> env_step(const DevModel<Real>& m, const EnvCfg<Real>& c, A
   }
   WARP_SYNC();
   const int warn = s.warn;
-  const float sn = (float)s.sum_nefc, sc = (float)s.sum_ncon, si = (float)s.sum_iter;
+  const int sn = s.sum_nefc, sc = s.sum_ncon, si = s.sum_iter;
   update_cache(m, c, s);
   ContactFlags cf = contact_flags(m, c, s);
   write_obs(m, c, s, cf);
   StepOut<Real> r = reward_done(m, c, s, cf, act);
   IF_LANE0 {
     s.st.ep_return += r.reward;
-    float* st = s.st.stat;
-    st[ST_NEFC] += sn; st[ST_NCON] += sc; st[ST_ITER] += si; st[ST_SUBSTEPS] += (float)c.frame_skip;
-    if (warn) st[ST_UNSTABLE] += 1;
-    if (s.overflow) st[ST_OVERFLOW] += 1;
+    auto* st = s.st.stat;
+    st[ST_NEFC].i += sn; st[ST_NCON].i += sc; st[ST_ITER].i += si; st[ST_SUBSTEPS].i += c.frame_skip;
+    if (warn) st[ST_UNSTABLE].i += 1;
+    if (s.overflow) st[ST_OVERFLOW].i += 1;
     if (r.terminated || r.truncated) {
-      st[ST_EPISODES] += 1; st[ST_RETURN] += (float)s.st.ep_return; st[ST_LENGTH] += (float)s.st.t;
-      if (r.terminated && r.reason) st[r.reason] += 1;
-      if (r.truncated && !r.terminated) st[ST_TRUNC] += 1;
+      st[ST_EPISODES].i += 1; st[ST_RETURN].f += (float)s.st.ep_return; st[ST_LENGTH].i += s.st.t;
+      if (r.terminated && r.reason) st[r.reason].i += 1;
+      if (r.truncated && !r.terminated) st[ST_TRUNC].i += 1;
     }
   }
   WARP_SYNC();
