@@ -95,7 +95,8 @@ int ur3e_batch_set_sensor_buffer(ur3e_batch* b, void* sensors_dev);
 /* episode statistics + solver counters since the last reset of the counters: 16 doubles (see UR3E_STAT_*) summed over the batch */
 int ur3e_batch_stats(ur3e_batch* b, double* stats16_dev, int reset_counters, void* stream);
 enum { UR3E_STAT_EPISODES = 0, UR3E_STAT_RETURN, UR3E_STAT_LENGTH, UR3E_STAT_SUCCESS, UR3E_STAT_TERM_REACH, UR3E_STAT_TERM_TOPPLE,
-       UR3E_STAT_TERM_COLLISION, UR3E_STAT_TRUNC, UR3E_STAT_UNSTABLE, UR3E_STAT_NEFC, UR3E_STAT_NCON, UR3E_STAT_ITER, UR3E_STAT_SUBSTEPS, UR3E_STAT_OVERFLOW };
+       UR3E_STAT_TERM_COLLISION, UR3E_STAT_TRUNC, UR3E_STAT_UNSTABLE, UR3E_STAT_NEFC, UR3E_STAT_NCON, UR3E_STAT_ITER, UR3E_STAT_SUBSTEPS, UR3E_STAT_OVERFLOW,
+       UR3E_STAT_PAD_CONTACT_STEPS /* env-steps that ended with >= 1 gripper-pad / mug contact */, UR3E_STAT_STEPS /* env-steps */ };
 /* d.* reads of one environment after a forward pass at its current state (mj_forward, mj_fullM, d.qfrc_bias, d.qacc,
  * d.ncon, d.contact[].dist/pos, mj_jacSite for the tcp): writes float64 host arrays; any pointer may be NULL */
 int ur3e_batch_debug_forward(ur3e_batch* b, int64_t env, double* M_nvnv, double* qfrc_bias, double* qacc, double* qfrc_constraint,
@@ -108,6 +109,11 @@ int ur3e_batch_kernel_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t* w
  * when the batch has a single size class.  Which tier steps an environment is decided per environment on the device (its own
  * recent contact / row counts), so trajectories do not depend on the batch size, the world size or host timing. */
 int ur3e_batch_tier_info(const ur3e_batch* b, int64_t* out8);
+/* Measurement aid (bench.py's roofline): while enabled, every step-kernel launch is bracketed by a cudaEvent pair on the launching
+ * stream.  ur3e_batch_kernel_times synchronises and returns {lite-tier kernel ms, lite-tier launches, full-tier kernel ms, full-tier
+ * launches} accumulated since the timing was enabled (a batch with one size class reports it as the full tier). */
+int ur3e_batch_kernel_timing(ur3e_batch* b, int enable);
+int ur3e_batch_kernel_times(ur3e_batch* b, double* out4);
 /* bytes of the persistent per-environment record in HBM (read + written once per step) */
 int ur3e_batch_state_bytes(const ur3e_batch* b);
 

@@ -104,5 +104,6 @@ def test_sharding_and_stats_allreduce_gloo_world2():
     n, s = q.get(timeout=120)
     [p.join(60) for p in procs]
     assert n == total and s == sum(range(total))
-    d = D.summarize(torch.tensor([4.0, 10.0, 40.0, 1.0] + [0.0] * 12), lib.STAT_NAMES + ["", ""])
+    d = D.summarize(torch.tensor([4.0, 10.0, 40.0, 1.0] + [0.0] * 12), lib.STAT_NAMES)
+    assert len(lib.STAT_NAMES) == 16
     assert d["mean_return"] == 2.5 and d["mean_length"] == 10 and d["success_rate"] == 0.25

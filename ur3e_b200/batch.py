@@ -141,6 +141,16 @@ class SimBatch:
                              lite_tier_steps=int(t[4]), full_only_steps=int(t[5]), last_overflow_envs=int(t[6]))
         return d
 
+    def kernel_timing(self, enable=True):
+        """Bracket every step-kernel launch with CUDA events on the launching stream (measurement aid, see kernel_times)."""
+        _lib.check(self._L.ur3e_batch_kernel_timing(self.ptr, int(enable)), "ur3e_batch_kernel_timing")
+
+    def kernel_times(self):
+        """{tier: (total ms, launches)} of the step kernels since kernel_timing(True); synchronises."""
+        v = (C.c_double * 4)()
+        _lib.check(self._L.ur3e_batch_kernel_times(self.ptr, v), "ur3e_batch_kernel_times")
+        return {"lite": (v[0], int(v[1])), "full": (v[2], int(v[3]))}
+
     def close(self):
         if getattr(self, "ptr", None):
             self._L.ur3e_batch_destroy(self.ptr)

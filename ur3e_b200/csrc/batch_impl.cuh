@@ -227,6 +227,8 @@ struct Batch : BatchBase {
     cudaSetDevice(device);
     cudaFree(d_ovf_count); cudaFree(d_ovf_list); if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev); if (order_ev) cudaEventDestroy(order_ev);
     cudaFree(d_model); cudaFree(d_consts); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
+    for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : ev_pool) cudaEventDestroy(e);
     if (own_stream) cudaStreamDestroy(own_stream);
     if (own_stream2) cudaStreamDestroy(own_stream2);
   }
@@ -341,10 +343,33 @@ struct Batch : BatchBase {
     KArgs<Real> a = base; a.op = OP_RESET; a.mask = mask; a.seed = sd; a.obs = (Real*)obs;
     return launch(a, s, n);
   }
+  // ---- optional per-launch timing (cudaEvent pairs on the launching stream)
+  struct Timed { cudaEvent_t a, b; int tier; };
+  bool timing = false; std::vector<Timed> timed; std::vector<cudaEvent_t> ev_pool; double t_ms[2] = {0, 0}; long long t_n[2] = {0, 0};
+  int kernel_timing(int enable) override {
+    double tmp[4]; if (int rc = kernel_times(tmp)) return rc;   // drain
+    t_ms[0] = t_ms[1] = 0; t_n[0] = t_n[1] = 0; timing = enable != 0;
+    return 0;
+  }
+  int kernel_times(double* out4) override {
+    CUDA_OK(cudaSetDevice(device));
+    for (auto& t : timed) {
+      CUDA_OK(cudaEventSynchronize(t.b));
+      float ms = 0; CUDA_OK(cudaEventElapsedTime(&ms, t.a, t.b));
+      t_ms[t.tier] += ms; t_n[t.tier] += 1; ev_pool.push_back(t.a); ev_pool.push_back(t.b);
+    }
+    timed.clear();
+    out4[0] = t_ms[0]; out4[1] = (double)t_n[0]; out4[2] = t_ms[1]; out4[3] = (double)t_n[1];
+    return 0;
+  }
+  int get_event(cudaEvent_t* e) { if (!ev_pool.empty()) { *e = ev_pool.back(); ev_pool.pop_back(); return 0; } CUDA_OK(cudaEventCreate(e)); return 0; }
   template <typename DD> int launch_step(KArgs<Real>& a, cudaStream_t s, unsigned blocks) {
     constexpr int W = warps_per_block<Real, DD>();
+    Timed t{nullptr, nullptr, (HAS_LITE && std::is_same<DD, DL>::value) ? 0 : 1};
+    if (timing) { if (int rc = get_event(&t.a)) return rc; if (int rc = get_event(&t.b)) return rc; CUDA_OK(cudaEventRecord(t.a, s)); }
     if (a.sens) step_kernel<Real, DD, true><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
     else step_kernel<Real, DD><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
+    if (timing) { CUDA_OK(cudaEventRecord(t.b, s)); timed.push_back(t); }
     ++launches;
     CUDA_OK(cudaGetLastError());
     return 0;

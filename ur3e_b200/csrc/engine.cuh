@@ -42,10 +42,11 @@ enum RowType { ROW_EQ = 0, ROW_EQJ = 1, ROW_FRICTION = 2, ROW_LIMIT_LO = 3, ROW_
 
 // Persistent per-environment record (lives in HBM between launches, one contiguous 16-byte aligned block per
 // environment so that a warp loads/stores it with coalesced 128-bit accesses).
-constexpr int NSTAT = 14;
+constexpr int NSTAT = 16;
 constexpr int MAX_FRAME_SKIP = 256;   // 256 substeps x 112 rows < 2^15: the per-step row / contact / iteration sums are 16-bit
 enum StatSlot { ST_EPISODES = 0, ST_RETURN, ST_LENGTH, ST_SUCCESS, ST_TERM_REACH, ST_TERM_TOPPLE, ST_TERM_COLLISION, ST_TRUNC, ST_UNSTABLE,
-                ST_NEFC, ST_NCON, ST_ITER, ST_SUBSTEPS, ST_OVERFLOW };
+                ST_NEFC, ST_NCON, ST_ITER, ST_SUBSTEPS, ST_OVERFLOW,
+                ST_PADCON /* env-steps that ended with at least one pad-mug contact */, ST_STEPS /* env-steps */ };
 template <typename Real, typename D>
 struct alignas(16) EnvState {
   Real qpos[D::NQ], qvel[D::NV], qacc_ws[D::NV];

@@ -315,6 +315,8 @@ UR3E_HD StepOut<Real> env_step(const DevModel<Real>& m, const EnvCfg<Real>& c, A
     st[ST_NEFC].i += sn; st[ST_NCON].i += sc; st[ST_ITER].i += si; st[ST_SUBSTEPS].i += c.frame_skip;
     if (warn) st[ST_UNSTABLE].i += 1;
     if (s.overflow) st[ST_OVERFLOW].i += 1;
+    st[ST_STEPS].i += 1;
+    if (cf.grasp_count > 0) st[ST_PADCON].i += 1;
     if (r.terminated || r.truncated) {
       st[ST_EPISODES].i += 1; st[ST_RETURN].f += (float)s.st.ep_return; st[ST_LENGTH].i += s.st.t;
       if (r.terminated && r.reason) st[r.reason].i += 1;
