@@ -41,7 +41,7 @@ def parse():
     p.add_argument("--workload", default="rollout", choices=["rollout", "reach", "mug"])
     p.add_argument("--envs-per-gpu", type=int, default=0)
     p.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    p.add_argument("--settle", type=int, default=-1, help="untimed env-steps before the warm-up (-1 = the workload's default: rollout 3000, mug 1200, reach 1000)")
+    p.add_argument("--settle", type=int, default=-1, help="untimed env-steps before the warm-up (-1 = the workload's default: rollout 3000, mug 1500, reach 1000)")
     p.add_argument("--cpu-steps", type=int, default=0, help="env-steps per CPU worker for the cpu_baseline sample (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -52,9 +52,9 @@ def parse():
 
 
 WORKLOADS = {
-    "rollout": dict(envs=65536, settle=3000, desc="config 3: gymnasium_env/ur3e-v2 rollout collection on main.xml, U(action_space) actions, auto-reset, frame_skip 2, dt 1 ms, steady state"),
+    "rollout": dict(envs=65536, settle=3000, desc="config 3: gymnasium_env/ur3e-v2 rollout collection on main.xml, U(action_space) actions, auto-reset, frame_skip 2, dt 1 ms, steady state (episode phases staggered over the 2500-step horizon)"),
     "reach": dict(envs=4096, settle=1000, desc="config 2: ur3e_2f85.xml task-space reach, pid_task_ctrl every mj_step, target re-drawn every 500 steps, contact-free, frame_skip 1, dt 1 ms"),
-    "mug": dict(envs=16384, settle=1200, desc="config 4: main.xml scripted pick-and-lift (move_l_mug.py / build_traj_l_pick_place targets, per environment) through the ur3e-v2 wrapper, frame_skip 2; approach untimed, timed region = grasp / lift / carry with gripper-mug contacts"),
+    "mug": dict(envs=16384, settle=1500, desc="config 4: main.xml scripted pick-and-lift (move_l_mug.py / build_traj_l_pick_place targets; per-environment start delay, pick jitter, lift height) through the ur3e-v2 wrapper, frame_skip 2; approach untimed, timed region = grasp / lift / carry with gripper-mug contacts"),
 }
 
 
@@ -152,17 +152,23 @@ class Workload:
         else:
             self.model = Model(asset("main.xml")); self.mname = "C"
             _, kw, _, _ = presets.ENV_SPECS["gymnasium_env/ur3e-v2"]
-            self.cfg = presets.make_config(self.model, kw, auto_reset=1, env_id_base=rank * n, reset_noise=lib.NOISE_HIGH if name == "rollout" else lib.NOISE_LOW,
+            # mug: the reference script resets deterministically (move_l_mug.py:34 reset_with_mug(..., "deterministic", "down")); its open-loop
+            # expert does not survive the env's reset noise.  Diversity between environments comes from per-environment script
+            # delays, pick jitter and lift heights instead (see _mug_script_setup).
+            self.cfg = presets.make_config(self.model, kw, auto_reset=1, env_id_base=rank * n, reset_noise=lib.NOISE_HIGH if name == "rollout" else lib.NOISE_NONE,
                                            solver_iterations=args.solver_iters)
         self.batch = SimBatch(self.model, self.cfg, n, local, dtype)
         self.obs0 = self.batch.reset(seed=0).clone()
         g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+        self.gen = g
         self.acts = None
         if name == "rollout":
             lo, hi = presets.action_bounds(self.model, "gymnasium_env/ur3e-v2")
             lo_t, hi_t = torch.tensor(lo, device=dev, dtype=dtype), torch.tensor(hi, device=dev, dtype=dtype)
             self.acts = [(lo_t + (hi_t - lo_t) * torch.rand(n, 4, device=dev, dtype=dtype, generator=g)).contiguous() for _ in range(self.NBUF)]
             self.period = 1            # i.i.d. per step (= action_space.sample() as in init_gym.py:35)
+            self.stagger = int(self.cfg.max_steps)
+            self.env_phase = torch.randint(0, self.stagger, (n,), generator=g, device=dev)
         elif name == "reach":
             tcp = torch.tensor([0.29799994, 0.13349916, 0.1682003], device=dev, dtype=dtype)   # tcp at keyframe 'down' (assets/main.xml:415)
             self.acts = []
@@ -177,29 +183,44 @@ class Workload:
 
     # ---- mug: the reference's scripted expert, per environment (move_l_mug.py:36-41, build_traj.py:28-59, 187-229)
     HOLD, NPTS = 60, 15                # hold 120 mj_steps per waypoint = 60 env-steps at frame_skip 2; 15 waypoints per segment
+    MAX_DELAY = 300
     def _mug_script_setup(self):
         t = self.torch
         o = self.batch.obs
-        start = t.cat([o[:, 0:3], t.zeros(self.n, 1, device=self.dev, dtype=self.dtype)], 1)            # tcp at reset, gripper open
-        pick = t.cat([o[:, 3:6], t.full((self.n, 1), 0.5, device=self.dev, dtype=self.dtype)], 1)         # the mug's centre, gripper half closed
-        up = pick.clone(); up[:, 2] += 0.15; up[:, 3] = 1.0                                                # lift 0.15 m, gripper closed
-        place = t.cat([o[:, 6:9], t.ones(self.n, 1, device=self.dev, dtype=self.dtype)], 1); place[:, 2] += 0.025
+        n, kw = self.n, dict(device=self.dev, dtype=self.dtype)
+        jit = (t.rand(n, 2, generator=self.gen, **kw) - 0.5) * 0.003                                      # pick jitter +-1.5 mm in x, y
+        lift = 0.10 + 0.08 * t.rand(n, generator=self.gen, **kw)                                           # lift height 0.10 .. 0.18 m (the reference: 0.15)
+        start = t.cat([o[:, 0:3], t.zeros(n, 1, **kw)], 1)                                                 # tcp at reset, gripper open
+        pick = t.cat([o[:, 3:6], t.full((n, 1), 0.5, **kw)], 1); pick[:, 0:2] += jit                       # the mug's centre, gripper half closed
+        up = pick.clone(); up[:, 2] += lift; up[:, 3] = 1.0                                                # lift, gripper closed
+        place = t.cat([o[:, 6:9], t.ones(n, 1, **kw)], 1); place[:, 2] += 0.025
         drop = place.clone(); drop[:, 3] = 0.0
-        self.way = [start, pick, up, place, drop]
+        self.way = t.stack([start, pick, up, place, drop])                                                 # [5, n, 4]
+        self.delay = t.randint(0, self.MAX_DELAY, (n,), generator=self.gen, device=self.dev)               # every environment starts its script a little later
         self.script_len = 4 * self.HOLD * self.NPTS
+        self.env_idx = t.arange(n, device=self.dev)
 
     def action(self, k):
         if self.acts is not None:
             return self.acts[(k // self.period) % self.NBUF]
-        k = k % self.script_len
-        seg, r = divmod(k, self.HOLD * self.NPTS)
-        frac = (r // self.HOLD + 1) / self.NPTS
-        a, b = self.way[seg], self.way[seg + 1]
+        t = self.torch
+        ke = (k % (self.script_len + self.MAX_DELAY) - self.delay).clamp(0, self.script_len - 1)
+        seg = ke // (self.HOLD * self.NPTS)
+        frac = (((ke % (self.HOLD * self.NPTS)) // self.HOLD + 1).to(self.dtype) / self.NPTS).unsqueeze(1)
+        a, b = self.way[seg, self.env_idx], self.way[seg + 1, self.env_idx]
         return (a + (b - a) * frac).contiguous()
 
-    def step(self, k):
-        if self.acts is None and k > 0 and k % self.script_len == 0:       # script wrapped: start the next pick-and-place from a reset
+    def wrap(self, k):
+        """mug: the script (plus the largest delay) is over -- start the next pick-and-place from a reset"""
+        if self.acts is None and k > 0 and k % (self.script_len + self.MAX_DELAY) == 0:
             self.batch.reset(seed=k); self._mug_script_setup()
+
+    def step(self, k):
+        self.wrap(k)
+        if self.name == "rollout" and k < self.stagger:
+            # steady state of a long collection run: episode phases are spread over the 2500-step horizon (here by resetting 1/2500 of
+            # the batch at each of the first 2500 settle steps), so that every step sees its share of truncations + auto-resets
+            self.batch.reset(seed=1000 + k, mask=(self.env_phase == k))
         self.batch.step(self.action(k), want_final_obs=False)
 
 
@@ -226,14 +247,10 @@ def measure(w, steps, warmup, settle, flush, world, dist, sampler=None):
     for i in range(steps):
         if flush is not None:
             flush.zero_()                   # L2 flush between timed iterations (outside the per-step event pair)
-        if w.acts is None:
-            if k > 0 and k % w.script_len == 0:
-                b.reset(seed=k); w._mug_script_setup()
-            a = w.action(k)
-            if len(rec) < 64:
-                rec.append(a)
-        else:
-            a = w.action(k)
+        w.wrap(k)
+        a = w.action(k)
+        if w.acts is None and len(rec) < 64:
+            rec.append(a)
         ev[i][0].record()
         b.step(a, want_final_obs=False)
         ev[i][1].record()

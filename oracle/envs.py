@@ -30,6 +30,7 @@ class OracleEnv:
         root = m.id("body", "robotiq_base_mount")
         par = m.py["body_parentid"]
         self.gripper = {b for b in range(m.nbody) if self._is_desc(b, root, par)}
+        self.arm = {b for b in range(m.nbody) if self._is_desc(b, m.id("body", "robot_base"), par)}      # gym_utils.py:133-143 init_collision_cache
         self.frame_skip = {"v2": 2, "v0": 2, "indirect": 1, "direct": 2}[kind]
         self.max_steps = {"v2": 2500, "v0": 500, "indirect": 2500, "direct": 1200}[kind]
         self.gains = GAINS_V0 if kind == "v0" else GAINS_MUG
@@ -71,6 +72,15 @@ class OracleEnv:
         for c in self.d.contacts():
             b1, b2 = gb[c.geom1], gb[c.geom2]
             if (b1 in self.gripper and b2 == self.table) or (b2 in self.gripper and b1 == self.table):
+                return 1
+        return 0
+
+    def self_collision(self):
+        """gym_utils.py:146-172: two bodies of the robot_base subtree in contact, unless both belong to the gripper subtree."""
+        gb = self.m.py["geom_bodyid"]
+        for c in self.d.contacts():
+            b1, b2 = gb[c.geom1], gb[c.geom2]
+            if b1 in self.arm and b2 in self.arm and not (b1 in self.gripper and b2 in self.gripper):
                 return 1
         return 0
 
@@ -116,7 +126,7 @@ class OracleEnv:
             placement += 40
         danger = min(0, -100000000000 * (bc[2] - gp[2] + 0.5) ** 3)
         toppled = bc[2] <= max(self.mug_size[0], self.mug_size[1])
-        pen = -25 * self.table_collision() + -8 * toppled + -4 * max(0, pad_top) + danger   # self-collision needs meshes: 0
+        pen = -40 * self.self_collision() + -25 * self.table_collision() + -8 * toppled + -4 * max(0, pad_top) + danger   # ur3e_env.py:339-345
         return descent + align + grasp + lift + placement + 700.5 * grip * ready + 1700.5 * (gs == 2) * ready * np.tanh(10 * grip) + pen
 
     def step(self, action):
@@ -135,14 +145,14 @@ class OracleEnv:
             r = self.reward_v2(o, action)
             self.t += 1
             dpick = np.linalg.norm(o[:3] - o[3:6])
-            term = bool(dpick > 1 or o[5] <= topple_z)
+            term = bool(dpick > 1 or self.self_collision() or o[5] <= topple_z)
             trunc = self.t >= self.max_steps
             if np.linalg.norm(o[3:6] - o[6:9]) < 0.05:
                 term = True; r += 50.0
         elif self.kind == "v0":
             r = self.reward_v0(o, action)
             dpick = np.linalg.norm(o[:3] - o[3:6]); dplace = np.linalg.norm(o[3:6] - o[6:9])
-            term = bool(dplace < 0.005 or dpick > 1 or o[5] <= topple_z)
+            term = bool(dplace < 0.005 or dpick > 1 or self.self_collision() or o[5] <= topple_z)
             trunc = self.t >= self.max_steps
             self.t += 1
         else:

@@ -468,29 +468,19 @@ def _collision_pairs(m, excl, pairs):
                 raise NotImplementedError("only plane/box primitives are supported")
             b1, b2 = m["geom_bodyid"][g1], m["geom_bodyid"][g2]
             key = (g1, g2)
-            if key in explicit:
-                e1, e2, attr = explicit[key]
-                row = dict(g1=e1, g2=e2, condim=int(attr.get("condim", 3)),
-                           friction=_floats(attr.get("friction"), 5, [1, 1, 0.005, 0.0001, 0.0001]),
-                           solref=_floats(attr.get("solref"), 2, DEFAULT_SOLREF),
-                           solimp=_floats(attr.get("solimp"), 5, DEFAULT_SOLIMP),
-                           margin=float(attr.get("margin", 0)), gap=float(attr.get("gap", 0)))
-                if row["g1"] > row["g2"] and t1 != GEOM_PLANE:
-                    pass
-                out.append(row)
-                continue
-            w1, w2 = weld[b1], weld[b2]
-            if w1 == w2:
-                continue  # same body or welded together (both static included)
-            if not ((m["geom_contype"][g1] & m["geom_conaffinity"][g2]) or (m["geom_contype"][g2] & m["geom_conaffinity"][g1])):
-                continue
-            # parent-child filter on weld bodies (skipped when the parent is the static world weld 0)
-            pw1 = weld[parent[w1]] if w1 != 0 else -1
-            pw2 = weld[parent[w2]] if w2 != 0 else -1
-            if (w1 != 0 and w2 != 0) and (pw1 == w2 or pw2 == w1):
-                continue
-            if (min(b1, b2), max(b1, b2)) in exset:
-                continue
+            if key not in explicit:
+                w1, w2 = weld[b1], weld[b2]
+                if w1 == w2:
+                    continue  # same body or welded together (both static included)
+                if not ((m["geom_contype"][g1] & m["geom_conaffinity"][g2]) or (m["geom_contype"][g2] & m["geom_conaffinity"][g1])):
+                    continue
+                # parent-child filter on weld bodies (skipped when the parent is the static world weld 0)
+                pw1 = weld[parent[w1]] if w1 != 0 else -1
+                pw2 = weld[parent[w2]] if w2 != 0 else -1
+                if (w1 != 0 and w2 != 0) and (pw1 == w2 or pw2 == w1):
+                    continue
+                if (min(b1, b2), max(b1, b2)) in exset:
+                    continue
             p1, p2 = m["geom_priority"][g1], m["geom_priority"][g2]
             if p1 != p2:
                 gw = g1 if p1 > p2 else g2
@@ -503,11 +493,22 @@ def _collision_pairs(m, excl, pairs):
                 solref = mix * m["geom_solref"][g1] + (1 - mix) * m["geom_solref"][g2]
                 solimp = mix * m["geom_solimp"][g1] + (1 - mix) * m["geom_solimp"][g2]
                 condim = int(max(m["geom_condim"][g1], m["geom_condim"][g2]))
-            out.append(dict(g1=g1, g2=g2, condim=condim,
-                            friction=[fr[0], fr[0], fr[1], fr[2], fr[2]],
-                            solref=list(solref), solimp=list(solimp),
-                            margin=float(max(m["geom_margin"][g1], m["geom_margin"][g2])),
-                            gap=float(max(m["geom_gap"][g1], m["geom_gap"][g2]))))
+            row = dict(g1=g1, g2=g2, condim=condim,
+                       friction=[fr[0], fr[0], fr[1], fr[2], fr[2]],
+                       solref=list(solref), solimp=list(solimp),
+                       margin=float(max(m["geom_margin"][g1], m["geom_margin"][g2])),
+                       gap=float(max(m["geom_gap"][g1], m["geom_gap"][g2])))
+            if key in explicit:
+                # explicit <pair>: never filtered; attributes it does not set are inferred from its geoms (mjCPair::Compile)
+                e1, e2, attr = explicit[key]
+                row["g1"], row["g2"] = e1, e2
+                if "condim" in attr: row["condim"] = int(attr["condim"])
+                if "friction" in attr: row["friction"] = _floats(attr.get("friction"), 5, row["friction"])
+                if "solref" in attr: row["solref"] = _floats(attr.get("solref"), 2, row["solref"])
+                if "solimp" in attr: row["solimp"] = _floats(attr.get("solimp"), 5, row["solimp"])
+                if "margin" in attr: row["margin"] = float(attr["margin"])
+                if "gap" in attr: row["gap"] = float(attr["gap"])
+            out.append(row)
     # canonical order: plane first within a pair, list sorted by (g1, g2)
     for r in out:
         if m["geom_type"][r["g2"]] == GEOM_PLANE:

@@ -65,6 +65,7 @@ class MjData:
     qvel = property(lambda s: s._get("qvel"), lambda s, v: s._get("qvel").__setitem__(slice(None), v))
     ctrl = property(lambda s: s._get("ctrl"), lambda s, v: s._get("ctrl").__setitem__(slice(None), v))
     qacc = property(lambda s: s._get("qacc"))
+    qacc_warmstart = property(lambda s: s._get("qacc_warmstart"))
     qfrc_bias = property(lambda s: s._get("qfrc_bias"))
     xpos = property(lambda s: s._get("xpos").reshape(-1, 3))
     xmat = property(lambda s: s._get("xmat").reshape(-1, 9))

@@ -45,6 +45,78 @@ def test_env_episode_vs_reference_fixture_f64(kind):
     assert rel(qpos[0].cpu().numpy(), g["qpos"][-1]) < 1e-4
 
 
+def test_pick_place_expert_episode_vs_reference_fixture_f64():
+    """BASELINE config 4 parity: the reference's scripted expert (move_l_mug.py targets, build_traj_l_pick_place) run through the
+    reference's own UR3eEnv2 class for a whole episode -- approach, grasp (up to 16 contacts), lift 6 cm, carry towards the ghost,
+    truncation at step 2500 -- tests/golden/env_v2_pick.npz.  float64 CUDA build from the fixture's initial state, NO re-seeding:
+    every observation and reward of the 2500 steps within 1e-4 relative, same robust-grasp flags, same truncation step."""
+    g = np.load(GOLD + "/env_v2_pick.npz")
+    T = len(g["reward"])
+    assert T == 2500 and g["truncated"][-1] and not g["terminated"].any() and g["ncon"].max() >= 12 and g["obs"][:, 5].max() > 0.1
+    env = UR3eVecEnv(IDS["v2"], 2, dtype=torch.float64, auto_reset=False, reset_noise=lib.NOISE_NONE)
+    env.reset()
+    env.set_state(torch.tensor(np.tile(g["qpos0"], (2, 1)), device="cuda"), torch.tensor(np.tile(g["qvel0"], (2, 1)), device="cuda"))
+    acts = torch.tensor(g["actions"], device="cuda")
+    rec_o = torch.empty(T, 24, dtype=torch.float64, device="cuda"); rec_r = torch.empty(T, dtype=torch.float64, device="cuda")
+    flags = torch.empty(T, 2, dtype=torch.uint8, device="cuda")
+    for k in range(T):
+        obs, rew, term, trunc, _ = env.step(acts[k].expand(2, 4).contiguous())
+        rec_o[k] = obs[0]; rec_r[k] = rew[0]; flags[k, 0] = term[0]; flags[k, 1] = trunc[0]
+    o, r, f = rec_o.cpu().numpy(), rec_r.cpu().numpy(), flags.cpu().numpy()
+    err_o = np.abs(o - g["obs"]) / (np.abs(g["obs"]) + 1e-3)
+    err_r = np.abs(r - g["reward"]) / np.maximum(1.0, np.abs(g["reward"]))
+    assert np.array_equal(o[:, 23], g["obs"][:, 23])                       # robust-grasp flag on exactly the same 1511 steps
+    assert err_o.max() < 1e-4 and err_r.max() < 1e-4, (err_o.max(), int(err_o.max(axis=1).argmax()), err_r.max())
+    assert np.array_equal(f[:, 0].astype(bool), g["terminated"]) and np.array_equal(f[:, 1].astype(bool), g["truncated"])
+
+
+def test_pick_place_expert_succeeds_on_production_f32():
+    """The same script on the float32 production kernels (two tiers: the grasp runs on the full size class): the mug is grasped,
+    lifted and carried like in the reference episode (chaotic contact switching forbids a per-step bound over 2500 steps; the
+    stated bound is on the outcome: lift height within 5 mm, robust-grasp step count within 10 %, end position within 1 cm)."""
+    g = np.load(GOLD + "/env_v2_pick.npz")
+    T = len(g["reward"]); n = 8
+    env = UR3eVecEnv(IDS["v2"], n, dtype=torch.float32, auto_reset=False, reset_noise=lib.NOISE_NONE)
+    env.reset()
+    env.set_state(torch.tensor(np.tile(g["qpos0"], (n, 1)), device="cuda", dtype=torch.float32), torch.tensor(np.tile(g["qvel0"], (n, 1)), device="cuda", dtype=torch.float32))
+    acts = torch.tensor(g["actions"], device="cuda", dtype=torch.float32)
+    zmax = torch.zeros(n, device="cuda"); robust = torch.zeros(n, device="cuda")
+    for k in range(T):
+        obs, rew, term, trunc, _ = env.step(acts[k].expand(n, 4).contiguous())
+        zmax = torch.maximum(zmax, obs[:, 5]); robust += obs[:, 23]
+    assert torch.equal(obs[0], obs[n - 1])
+    assert abs(zmax[0].item() - g["obs"][:, 5].max()) < 5e-3
+    assert abs(robust[0].item() - g["obs"][:, 23].sum()) < 0.1 * g["obs"][:, 23].sum()
+    assert np.abs(obs[0, 3:6].cpu().numpy() - g["obs"][-1, 3:6]).max() < 1e-2
+    info = env.batch.kernel_info()["lite"]
+    assert info["lite_tier_steps"] == T and env.episode_stats()["overflow_steps"] == 0
+
+
+@pytest.mark.parametrize("kind", ["v2", "v0"])
+def test_folded_arm_self_collision_vs_oracle(kind):
+    """box hulls stand in for the arm's collision meshes; get_self_collision (gym_utils.py:146-172) fires when the elbow
+    folds the wrist onto the shoulder / upper arm: ur3e-v2 and ur3e-v0 terminate (ur3e_env2.py:244-246, ur3e_env.py:441-443), v0's
+    reward carries the -40 penalty (ur3e_env.py:340).  float64 CUDA build against the oracle env from the same injected state."""
+    from oracle import envs as OE
+    ref = OE.OracleEnv(asset("main.xml"), kind)
+    qp, qv = ref.m.key("down")
+    env = UR3eVecEnv(IDS[kind], 3, dtype=torch.float64, auto_reset=False, reset_noise=lib.NOISE_NONE)
+    env.reset()
+    Q = np.tile(qp, (3, 1)); Q[1, 2] = 2.8; Q[2, 2] = 2.9           # env 0 stays at 'down', 1 and 2 fold the elbow
+    env.set_state(torch.tensor(Q, device="cuda"), torch.tensor(np.tile(qv, (3, 1)), device="cuda"))
+    o0 = ref.reset()
+    a = np.hstack([o0[:3], 0.0])
+    obs, rew, term, trunc, _ = env.step(torch.tensor(np.tile(a, (3, 1)), device="cuda"))
+    for e in range(3):
+        ref.set_state(Q[e], qv)
+        assert ref.self_collision() == (1 if e else 0)
+        o, r, te, tr = ref.step(a)
+        assert bool(term[e]) == te == bool(e), (e, te)
+        assert rel(obs[e].cpu().numpy(), o) < 1e-4 and abs(rew[e].item() - r) < 1e-4 * max(1.0, abs(r))
+    st = env.episode_stats()
+    assert st["term_collision"] == 2 and st["episodes"] == 2
+
+
 @pytest.mark.parametrize("kind", ["v2", "v0", "indirect", "direct"])
 def test_truncation_step_vs_reference_fixture(kind):
     """ur3e-v2 increments t before the truncation test (first truncated step 2500), the other three test first

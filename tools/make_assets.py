@@ -37,6 +37,27 @@ MESH_INERTIA = {
                               diaginertia="2.0e-07 2.68e-07 6.9e-08"),
 }
 
+# Box hulls standing in for the collision meshes of the arm links and the gripper base (main.xml only: the scene of the gym envs).
+# The reference collides those meshes with the table, the mug and each other (dynamic pairs + its explicit <pair>s,
+# assets/main.xml:325-334) and reads the resulting contacts in get_self_collision / get_table_collision
+# (utils/gym_utils.py:146-201).  The STL files are not in the repository, so the dimensions below are estimates from
+# the link offsets in the XML and the UR3e / 2F-85 data sheets (tube radii 40 / 33 / 32 mm, base 55 mm), kept slightly inside the
+# real hulls so that no pose near keyframe 'down' reports a false self-collision.  geom name -> (body, pos, half-sizes).
+# Collision classes: proxies use contype = conaffinity = 2, the table plane and the mug 3, the pad boxes keep the reference's 1:
+# proxies collide with the table, the mug and each other (non-adjacent links) but not with the pad boxes, which bounds the candidate
+# pair list (48 pairs) -- pad-vs-arm-link contacts are the one family of the reference's dynamic pairs that is not modelled.
+PROXIES = {
+    "base":      ("robot_base",     "0 0 0.045",   "0.055 0.055 0.045"),
+    "shoulder":  ("shoulder_link",  "0 0.015 0",   "0.045 0.06 0.06"),
+    "upperarm":  ("upper_arm_link", "0 0 0.122",   "0.04 0.04 0.162"),
+    "forearm":   ("forearm_link",   "0 0 0.1065",  "0.033 0.033 0.1395"),
+    "wrist1":    ("wrist_1_link",   "0 0.015 0",   "0.032 0.055 0.032"),
+    "wrist2":    ("wrist_2_link",   "0 0 0.02",    "0.032 0.032 0.05"),
+    "wrist3":    ("wrist_3_link",   "0 0.03 0",    "0.032 0.05 0.032"),
+    "collision": ("gripper_base",   "0 0 0.045",   "0.017 0.036 0.045"),
+}
+PROXY_BITS, SHARED_BITS = "2", "3"
+
 MESH_CLASSES = {"visual", "collision"}  # default classes whose geoms are type="mesh"
 
 
@@ -46,7 +67,20 @@ def is_mesh_geom(g):
     return g.get("class") in MESH_CLASSES and g.get("type") is None
 
 
-def strip(root):
+def add_proxies(root):
+    """main.xml: box hulls for the stripped collision meshes (see PROXIES); must run before the <pair> pruning."""
+    bodies = {b.get("name"): b for b in root.iter("body")}
+    for name, (body, pos, size) in PROXIES.items():
+        g = ET.Element("geom", dict(name=name, type="box", pos=pos, size=size, mass="0", contype=PROXY_BITS, conaffinity=PROXY_BITS))
+        b = bodies[body]
+        idx = max([i for i, e in enumerate(list(b)) if e.tag in ("inertial", "joint", "site")] + [-1]) + 1
+        b.insert(idx, g)
+    for g in root.iter("geom"):
+        if g.get("name") in ("table", "fish"):
+            g.set("contype", SHARED_BITS); g.set("conaffinity", SHARED_BITS)
+
+
+def strip(root, proxies=False):
     removed = set()
     for tag in ("asset", "visual", "size"):
         for e in root.findall(tag):
@@ -68,6 +102,9 @@ def strip(root):
         for a in ("rgba", "material", "group"):
             if a in e.attrib:
                 del e.attrib[a]
+    if proxies:
+        add_proxies(root)
+        removed -= set(PROXIES)
     for body in root.iter("body"):
         name = body.get("name")
         if name in MESH_INERTIA and body.find("inertial") is None:
@@ -88,7 +125,7 @@ def main():
     for name in ("main.xml", "ur3e_2f85.xml", "ur3e_raw.xml"):
         tree = ET.parse(os.path.join(REF, "assets", name))  # ET drops comments
         root = tree.getroot()
-        removed = strip(root)
+        removed = strip(root, proxies=(name == "main.xml"))
         ET.indent(tree, space="  ")
         path = os.path.join(OUT, name)
         with open(path, "w") as f:

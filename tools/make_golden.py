@@ -66,6 +66,41 @@ def env_episode(cls_name, module, steps, seed, direct=False):
     return {k: np.asarray(v) for k, v in rec.items()}
 
 
+def pick_place_episode():
+    """The reference's scripted expert (controller/move_l_mug.py:36-41 targets through build_traj_l_pick_place, build_traj.py:28-59:
+    approach the mug's centre closing to 0.5, lift 0.15 m closing fully, carry to the ghost + 0.025, release), fed to UR3eEnv2.step
+    as [x, y, z, grip] with 15 waypoints per segment held 60 env-steps (= the script's hold of 120 mj_steps at frame_skip 2), from
+    the deterministic keyframe reset the script uses.  Runs until the env reports success (mug within 0.05 of the ghost)."""
+    mod = __import__("gymnasium_env.envs.ur3e_env2", fromlist=["UR3eEnv2"])
+    sink = io.StringIO()
+    np.random.seed(3)
+    with contextlib.redirect_stdout(sink):
+        env = mod.UR3eEnv2()
+        env.reset()
+        qp, qv = gu.get_init(env.model, "deterministic", "down")
+        env.set_state(np.array(qp, dtype=np.float64), np.array(qv, dtype=np.float64)); env.t = 0
+        o = env._get_obs()
+    start = np.hstack([o[0:3], 0.0]); pick = np.hstack([o[3:6], 0.5]); up = pick + [0, 0, 0.15, 0.5]
+    place = np.hstack([o[6:9], 1.0]) + [0, 0, 0.025, 0]; drop = place.copy(); drop[3] = 0.0
+    way = [start, pick, up, place, drop]
+    H, N, EVERY = 60, 15, 25
+    rec = dict(qpos0=env.data.qpos.copy(), qvel0=env.data.qvel.copy(), obs0=np.asarray(o, dtype=np.float64), actions=[], obs=[], reward=[], terminated=[], truncated=[],
+               seed_step=[], seed_qpos=[], seed_qvel=[], seed_ws=[], ncon=[])
+    for k in range(4 * H * N):
+        if k % EVERY == 0:
+            rec["seed_step"].append(k); rec["seed_qpos"].append(env.data.qpos.copy()); rec["seed_qvel"].append(env.data.qvel.copy())
+            rec["seed_ws"].append(np.array(env.data.qacc_warmstart, dtype=np.float64).copy())
+        seg, r = divmod(k, H * N)
+        a = way[seg] + (way[seg + 1] - way[seg]) * ((r // H + 1) / N)
+        with contextlib.redirect_stdout(sink):
+            o, rew, te, tr, _ = env.step(a)
+        rec["actions"].append(a); rec["obs"].append(np.asarray(o, dtype=np.float64)); rec["reward"].append(float(rew))
+        rec["terminated"].append(bool(te)); rec["truncated"].append(bool(tr)); rec["ncon"].append(int(env.data.ncon))
+        if te or tr:
+            break
+    return {k: np.asarray(v) for k, v in rec.items()}
+
+
 def truncation_steps():
     """Step index (1-based) at which each reference env class first reports truncated=True under a hold-still action:
     ur3e_env2.py:89-92 increments t before the test (2500), the others test first (ur3e_env.py:183-194 -> 501,
@@ -149,6 +184,11 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **rec)
         print(name, "steps", len(rec["reward"]), "sum reward %.6f" % rec["reward"].sum(), "grasp max", rec["obs"][:, 23 if rec["obs"].shape[1] == 24 else 9].max(),
               "term", rec["terminated"].any(), "trunc", rec["truncated"].any())
+    if not only or "env_v2_pick" in only:
+        rec = pick_place_episode()
+        np.savez_compressed(os.path.join(OUT, "env_v2_pick.npz"), **rec)
+        print("env_v2_pick steps", len(rec["reward"]), "sum reward %.4f" % rec["reward"].sum(), "robust-grasp steps", int(rec["obs"][:, 23].sum()), "max ncon", rec["ncon"].max(),
+              "max mug z %.4f" % rec["obs"][:, 5].max(), "terminated", bool(rec["terminated"][-1]))
     if not only or "truncation" in only:
         np.savez_compressed(os.path.join(OUT, "truncation.npz"), **truncation_steps())
     if only and "controllers" not in only:

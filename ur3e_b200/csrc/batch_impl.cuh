@@ -251,6 +251,23 @@ struct Batch : BatchBase {
     if (m.ngeom > D::NG || m.npair > D::NPAIR || m.nv > D::NV || m.nq > D::NQ || m.nu > D::NU) return set_err("model exceeds the kernel size class (geoms / pairs / dofs)");
     if (m.ndeq > 3 * D::MAXCONNECT) return set_err("model has more connect equalities than the kernel size class stores rows for");
     auto body = [&](const char* nm) { int b = h.name2id(OBJ_BODY, nm); return b >= 0 ? bmap[b] : -1; };
+    {  // the contact predicates of utils/gym_utils.py name bodies of the loaded model: classify every collidable geom by them
+      const auto& par = h.I("body_parentid"); const auto& gbid = h.I("geom_bodyid");
+      auto under = [&](int b, int root) { if (root < 0) return false; for (int a = b; a > 0; a = par[a]) if (a == root) return true; return false; };
+      const int arm = h.name2id(OBJ_BODY, "robot_base"), grip = h.name2id(OBJ_BODY, "robotiq_base_mount"), table = h.name2id(OBJ_BODY, "table"),
+                mug = h.name2id(OBJ_BODY, "fish"), lpad = h.name2id(OBJ_BODY, "left_pad"), rpad = h.name2id(OBJ_BODY, "right_pad");
+      for (int i = 0; i < m.ngeom; ++i) {
+        const int b = gbid[m.geom_src[i]];
+        int f = 0;
+        if (under(b, arm)) f |= GF_ARM;
+        if (under(b, grip)) f |= GF_GRIPPER;
+        if (b == table && table >= 0) f |= GF_TABLE;
+        if (b == mug && mug >= 0) f |= GF_MUG;
+        if (b == lpad && lpad >= 0) f |= GF_LPAD;
+        if (b == rpad && rpad >= 0) f |= GF_RPAD;
+        m.geom_flags[i] = f;
+      }
+    }
     CUDA_OK(cudaMalloc(&d_model, sizeof m)); CUDA_OK(cudaMemcpy(d_model, &m, sizeof m, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMalloc(&d_state, sizeof(EnvState<Real, D>) * n_envs)); CUDA_OK(cudaMemset(d_state, 0, sizeof(EnvState<Real, D>) * n_envs));
     std::memset(&base, 0, sizeof base);
@@ -264,15 +281,6 @@ struct Batch : BatchBase {
     c.site_tcp = tracked("tcp"); c.site_mug = tracked("handle_site"); c.site_pad = tracked("right_pad1_site");
     c.body_mug = body("fish"); c.body_ghost = body("ghost");
     c.body_lpad = body("left_pad"); c.body_rpad = body("right_pad"); c.body_table = body("table");
-    c.gripper_mask = 0;
-    {  // gym_utils.py:133-143: robotiq_base_mount and everything below it
-      const auto& par = h.I("body_parentid");
-      const int root = h.name2id(OBJ_BODY, "robotiq_base_mount");
-      if (root >= 0) {
-        const int outside = bmap[par[root]];   // a merged mount shares its new id with the arm link it is bolted to
-        for (int b = root; b < h.nbody; ++b) { int a = b; while (a > root) a = par[a]; if (a == root && bmap[b] != outside) c.gripper_mask |= 1u << bmap[b]; }
-      }
-    }
     c.finger_q = 6;  // utils/utils.py:319-326 reads d.qpos[6] / d.qvel[6]
     c.topple_z = 0;
     if (c.body_mug >= 0) {

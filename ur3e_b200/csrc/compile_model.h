@@ -129,7 +129,7 @@ DevModel<Real> compile_model(const HostModel& h) {
     if (gmap[g] >= 0) return gmap[g];
     req(ng < MAXG, "too many collidable geoms");
     int i = ng++; gmap[g] = i;
-    m.geom_body[i] = gb[g]; m.geom_kind[i] = gt[g] == GEOM_PLANE ? GK_PLANE : GK_BOX;
+    m.geom_body[i] = gb[g]; m.geom_kind[i] = gt[g] == GEOM_PLANE ? GK_PLANE : GK_BOX; m.geom_src[i] = g;
     cp(m.geom_pos[i], gpos, 3 * g, 3); cpmat(m.geom_mat[i], gquat, 4 * g); cp(m.geom_size[i], gsize, 3 * g, 3);
     m.geom_rbound[i] = gt[g] == GEOM_PLANE ? Real(0) : (Real)std::sqrt(gsize[3 * g] * gsize[3 * g] + gsize[3 * g + 1] * gsize[3 * g + 1] + gsize[3 * g + 2] * gsize[3 * g + 2]);
     return i;

@@ -9,8 +9,8 @@ constexpr int MAXB = 26;     // bodies incl. world
 constexpr int MAXV = 20;     // dofs
 constexpr int MAXQ = 21;     // generalized positions
 constexpr int MAXU = 7;      // actuators
-constexpr int MAXG = 8;      // collidable primitive geoms
-constexpr int MAXPAIR = 16;  // candidate geom pairs
+constexpr int MAXG = 16;     // collidable primitive geoms
+constexpr int MAXPAIR = 64;  // candidate geom pairs
 constexpr int MAXEQ = 3;     // equality constraints
 constexpr int MAXSITE = 4;   // tracked sites (tcp, handle, pad)
 constexpr int MAXNM = 128;   // nnz of lower-triangular M
@@ -22,6 +22,8 @@ constexpr int MAXEFC = 112;  // constraint rows per env
 enum JointKind { JK_NONE = 0, JK_HINGE = 1, JK_FREE = 2 };
 enum GeomKind { GK_PLANE = 0, GK_BOX = 1 };
 enum EqKind { EK_CONNECT = 0, EK_JOINT = 1 };
+// which of the bodies the reference's contact predicates name a collidable geom belongs to (utils/gym_utils.py:108-201)
+enum GeomFlag { GF_ARM = 1 /* robot_base subtree */, GF_GRIPPER = 2 /* robotiq_base_mount subtree */, GF_TABLE = 4, GF_MUG = 8, GF_LPAD = 16, GF_RPAD = 32 };
 
 // controller evaluated inside the kernel (reference controller/controller_func.py)
 enum CtrlMode {
@@ -61,7 +63,8 @@ struct DevModel {
   int M_i[MAXNM], M_j[MAXNM];
   int tri_ab[(MAXV + 1) * (MAXV + 2) / 2];  // (a << 8 | b), b <= a, row-major lower triangle of the (nv+1)^2 augmented matrix
   // collidable geoms
-  int geom_body[MAXG], geom_kind[MAXG];
+  int geom_body[MAXG], geom_kind[MAXG], geom_src[MAXG];   // geom_src: index of the geom in the loaded model
+  int geom_flags[MAXG];   // GeomFlag bits by the geom's body in the loaded (unmerged) model; set at batch creation
   Real geom_pos[MAXG][3], geom_mat[MAXG][9], geom_size[MAXG][3], geom_rbound[MAXG];
   // candidate pairs (geom1 = plane for plane-box)
   int pair_g1[MAXPAIR], pair_g2[MAXPAIR], pair_src_g1[MAXPAIR], pair_src_g2[MAXPAIR];

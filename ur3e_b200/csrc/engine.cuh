@@ -23,15 +23,17 @@ struct Dims {
   static constexpr int MAXCON = MAXCON_ > 0 ? MAXCON_ : 1, MAXEFC = MAXEFC_ > 0 ? MAXEFC_ : 1;
   static constexpr bool HAS_CONTACT = MAXCON_ > 0;
   static constexpr int NS = MAXSITE;
-  static constexpr int NGRP = MAXEQ + NPAIR;
+  // candidate pairs that survive the broad phase get a narrow-phase slot; more than MAXACT at once counts as an overflow
+  static constexpr int MAXACT = !HAS_CONTACT ? 1 : (NPAIR < (MAXCON_ <= 8 ? 16 : 24) ? NPAIR : (MAXCON_ <= 8 ? 16 : 24));
+  static constexpr int NGRP = MAXEQ + (NPAIR < MAXCON ? NPAIR : MAXCON);   // one row group per connect equality / pair with contacts
   static constexpr int MAXCONNECT = 2;   // connect equalities a size class stores rows for (the 2F85 has two; checked at batch creation)
   static constexpr int MAXDENSE = HAS_CONTACT ? 3 * MAXCONNECT + 3 * MAXCON : 1;   // stored Jacobian rows
 };
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // body counts are after fixed-body merging (merge_bodies.h)          // assets/ur3e_raw.xml
 using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 12, 56>;    // assets/ur3e_2f85.xml
 using DimsGripExact = Dims<17, 14, 14, 7, 6, 12, 12, 56, 14, true>;   // the same caps, compiled for exactly ur3e_2f85.xml's sizes (float32 only)
-using DimsMain = Dims<19, 20, 21, 7, 6, 13, 24, 96, 14>;   // assets/main.xml (collidable geoms: four pad boxes, the mug, the table plane)
-using DimsMainLite = Dims<19, 20, 21, 7, 6, 13, 8, 44, 14, true>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
+using DimsMain = Dims<19, 20, 21, 7, 14, 48, 24, 96, 14>;   // assets/main.xml (collidable geoms: four pad boxes, the mug, the table plane, eight link hulls)
+using DimsMainLite = Dims<19, 20, 21, 7, 14, 48, 8, 44, 14, true>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 constexpr int STAGE_W = 3 + 4 * STAGE_PTS;
@@ -78,16 +80,13 @@ struct Arena {
   struct { Real frame[D::MAXCON][9]; } cu;   // contact frames: normal, two tangents.  The solver keeps each contact's cone Hessian (6 values)
                                              // in the tangents' storage (frame[c] + 3); the normal survives for the touch sensors
   Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_jv[D::MAXEFC], efc_Dact[D::MAXEFC];
-  union {   // geom frames are dead once the contacts exist; the solver's force / residual vectors reuse their storage
-    struct { Real efc_force[D::MAXEFC], efc_jar[D::MAXEFC]; };
-    struct { Real geom_xpos[D::NG][3], geom_xmat[D::NG][9]; };
-  };
+  Real efc_force[D::MAXEFC], efc_jar[D::MAXEFC];
   uint8_t con_pair[D::MAXCON], con_row[D::MAXCON];
   uint8_t efc_type[D::MAXEFC], efc_id[D::MAXEFC];
   // row groups sharing one column set (a connect equality, the joint equality, the contacts of one geom pair)
   int grp_mask[D::NGRP];
   uint8_t grp_row0[D::NGRP], grp_nrow[D::NGRP];
-  uint8_t stage_n[D::NPAIR], stage_off[D::NPAIR];
+  uint8_t stage_n[D::MAXACT], stage_off[D::MAXACT], act_pair[D::MAXACT];   // narrow-phase slots: contacts found, offset in the contact list, candidate pair
   Real eqj_deriv[MAXEQ];
   // per dof: its sparse rows (255 = none) so that the solver's inner loops never touch the model tables
   uint8_t sp_fl[D::NV], sp_lo[D::NV], sp_hi[D::NV], sp_ej[D::NV];
@@ -99,7 +98,7 @@ struct Arena {
   union alignas(16) {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
     struct { Real lmat[D::NB][9], lpos[D::NB][3]; } kin;   // kinematics only: each body's frame relative to its parent
-    Real stage[D::NPAIR][STAGE_W];   // per candidate pair: shared normal (3), then up to STAGE_PTS x (pos 3, dist 1)
+    Real stage[D::MAXACT][STAGE_W];   // per narrow-phase slot: shared normal (3), then up to STAGE_PTS x (pos 3, dist 1)
     Real efc_J[D::MAXDENSE][D::NV];   // dense rows only
   } u;
 };
@@ -260,7 +259,8 @@ template <typename Real> UR3E_HD void mat_mul3(Real* r, const Real* a, const Rea
 // 3x3 product spread over 12 lanes per body:
 //   A. every body in parallel: its frame relative to the parent, (L_b, t_b) = body offset * joint transform
 //   B. level by level: R_b = R_p L_b, x_b = x_p + R_p t_b   (lane = one entry of R_b or x_b)
-//   C. every body / geom / site in parallel: inertial frame position, joint axis (cdof), geom and site frames
+//   C. every body / site in parallel: inertial frame position, joint axis (cdof), site frames (geom frames are built by the
+//      collision lanes that need them)
 template <typename Real, typename D>
 UR3E_HD void kin_frames(const DevModel<Real>& m, Arena<Real, D>& s) {   // stages A and B: xpos, xmat of every body
   auto& kin = s.u.kin;
@@ -315,7 +315,7 @@ UR3E_HD void kin_frames(const DevModel<Real>& m, Arena<Real, D>& s) {   // stage
 template <typename Real, typename D>
 UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
   kin_frames(m, s);
-  WARP_FOR(i, nb_<D>(m) + ng_<D>(m) + nsite_<D>(m)) {
+  WARP_FOR(i, nb_<D>(m) + nsite_<D>(m)) {
     if (i < nb_<D>(m)) {
       const int b = i;
       if (b > 0) {
@@ -341,13 +341,8 @@ UR3E_HD void kinematics(const DevModel<Real>& m, Arena<Real, D>& s) {
           }
         }
       }
-    } else if (i < nb_<D>(m) + ng_<D>(m)) {
-      const int g = i - nb_<D>(m), b = m.geom_body[g]; Real v[3];
-      mat_vec3(v, s.fr.k.xmat[b], m.geom_pos[g]);
-      for (int k = 0; k < 3; ++k) s.geom_xpos[g][k] = s.xpos[b][k] + v[k];
-      mat_mul3(s.geom_xmat[g], s.fr.k.xmat[b], m.geom_mat[g]);
     } else {
-      const int j = i - nb_<D>(m) - ng_<D>(m), b = m.site_body[j]; Real v[3];
+      const int j = i - nb_<D>(m), b = m.site_body[j]; Real v[3];
       mat_vec3(v, s.fr.k.xmat[b], m.site_pos[j]);
       for (int k = 0; k < 3; ++k) s.site_xpos[j][k] = s.xpos[b][k] + v[k];
       if (j == 0) mat_mul3(s.site_xmat[0], s.fr.k.xmat[b], m.site_mat[0]);
@@ -592,42 +587,78 @@ UR3E_PHASE int box_box(const Real* p1, const Real* R1, const Real* s1, const Rea
   return cnt;
 }
 
+// world position of geom g (its body's frame is still alive during the collision phase)
+template <typename Real, typename D>
+UR3E_HD void geom_world_pos(const DevModel<Real>& m, const Arena<Real, D>& s, int g, Real* x) {
+  const int b = m.geom_body[g]; Real v[3];
+  mat_vec3(v, s.fr.k.xmat[b], m.geom_pos[g]);
+  for (int k = 0; k < 3; ++k) x[k] = s.xpos[b][k] + v[k];
+}
+
+// Broad phase over the model's static candidate list (lane = pair; bounding spheres / plane distance), then the narrow phase on
+// the survivors only (lane = survivor; plane-box, box-box SAT + clipping), then compaction into the contact list in pair order.
 template <typename Real, typename D>
 UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
   if constexpr (!D::HAS_CONTACT) { s.ncon = 0; return; }
   else {
-    WARP_FOR(p, np_<D>(m)) {
-      int g1 = m.pair_g1[p], g2 = m.pair_g2[p];
-      Real margin = m.pair_margin[p];
-      int n = 0;
-      const Real *x1 = s.geom_xpos[g1], *x2 = s.geom_xpos[g2];
-      if (m.geom_kind[g1] == GK_PLANE) {
-        const Real* pm = s.geom_xmat[g1];
-        Real h = (x2[0] - x1[0]) * pm[2] + (x2[1] - x1[1]) * pm[5] + (x2[2] - x1[2]) * pm[8];
-        if (h - m.geom_rbound[g2] <= margin) n = plane_box(x1, pm, x2, s.geom_xmat[g2], m.geom_size[g2], margin, s.u.stage[p]);
-      } else {
-        Real dd[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]}, r = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
-        if (dot3(dd, dd) <= r * r) n = box_box(x1, s.geom_xmat[g1], m.geom_size[g1], x2, s.geom_xmat[g2], m.geom_size[g2], margin, s.u.stage[p]);
+    const int np = np_<D>(m);
+    int nact = 0;
+    for (int base = 0; base < np; base += 32) {
+      const int cnt = np - base < 32 ? np - base : 32;
+      int bits = 0;
+      WARP_FOR(i, cnt) {
+        const int p = base + i, g1 = m.pair_g1[p], g2 = m.pair_g2[p];
+        const Real margin = m.pair_margin[p];
+        Real x1[3], x2[3]; geom_world_pos(m, s, g1, x1); geom_world_pos(m, s, g2, x2);
+        const Real dd[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
+        bool hit;
+        if (m.geom_kind[g1] == GK_PLANE) {
+          // plane normal = third column of its frame
+          const Real* R = s.fr.k.xmat[m.geom_body[g1]]; const Real* G = m.geom_mat[g1];
+          const Real nrm[3] = {R[0] * G[2] + R[1] * G[5] + R[2] * G[8], R[3] * G[2] + R[4] * G[5] + R[5] * G[8], R[6] * G[2] + R[7] * G[5] + R[8] * G[8]};
+          hit = dot3(dd, nrm) - m.geom_rbound[g2] <= margin;
+        } else {
+          const Real r = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
+          hit = dot3(dd, dd) <= r * r;
+        }
+        if (hit) bits |= (int)(1u << i);
       }
+      bits = warp_or(bits);
+      WARP_FOR(i, cnt) {
+        if ((bits >> i) & 1) { const int slot = nact + popcount32(bits & (int)((1u << i) - 1u)); if (slot < D::MAXACT) s.act_pair[slot] = (uint8_t)(base + i); }
+      }
+      nact += popcount32(bits);
+    }
+    if (nact > D::MAXACT) { nact = D::MAXACT; IF_LANE0 s.overflow |= 1; }
+    WARP_SYNC();
+    WARP_FOR(a, nact) {
+      const int p = s.act_pair[a], g1 = m.pair_g1[p], g2 = m.pair_g2[p];
+      const Real margin = m.pair_margin[p];
+      Real x1[3], x2[3], R1[9], R2[9];
+      geom_world_pos(m, s, g1, x1); geom_world_pos(m, s, g2, x2);
+      mat_mul3(R1, s.fr.k.xmat[m.geom_body[g1]], m.geom_mat[g1]); mat_mul3(R2, s.fr.k.xmat[m.geom_body[g2]], m.geom_mat[g2]);
+      Real* st = s.u.stage[a];
+      int n;
+      if (m.geom_kind[g1] == GK_PLANE) n = plane_box(x1, R1, x2, R2, m.geom_size[g2], margin, st);
+      else n = box_box(x1, R1, m.geom_size[g1], x2, R2, m.geom_size[g2], margin, st);
       int keep = 0;   // MuJoCo keeps a contact only when dist < margin
-      Real* st = s.u.stage[p];
       for (int c = 0; c < n; ++c) if (st[3 + 4 * c + 3] < margin) { if (keep != c) for (int k = 0; k < 4; ++k) st[3 + 4 * keep + k] = st[3 + 4 * c + k]; ++keep; }
-      s.stage_n[p] = (uint8_t)keep;
+      s.stage_n[a] = (uint8_t)keep;
     }
     WARP_SYNC();
     int total = 0;
-    for (int p = 0; p < np_<D>(m); ++p) { int n = s.stage_n[p]; IF_LANE0 s.stage_off[p] = (uint8_t)total; total += n; }
+    for (int a = 0; a < nact; ++a) { int n = s.stage_n[a]; IF_LANE0 s.stage_off[a] = (uint8_t)total; total += n; }
     const int capc = s.cap_con;   // <= D::MAXCON; smaller only when the caller lowers the cap (ur3e_env_config.lite_max_contacts)
     int ncon = total > capc ? capc : total;
     IF_LANE0 { s.ncon = ncon; if (total > capc) s.overflow |= 1; }
     WARP_SYNC();
-    WARP_FOR(i, np_<D>(m) * STAGE_PTS) {
-      int p = i / STAGE_PTS, c = i % STAGE_PTS;
-      int o = s.stage_off[p] + c;
-      if (c < s.stage_n[p] && o < capc) {
-        const Real* src = s.u.stage[p];
+    WARP_FOR(i, nact * STAGE_PTS) {
+      int a = i / STAGE_PTS, c = i % STAGE_PTS;
+      int o = s.stage_off[a] + c;
+      if (c < s.stage_n[a] && o < capc) {
+        const Real* src = s.u.stage[a];
         for (int k = 0; k < 3; ++k) { s.con_pos[o][k] = src[3 + 4 * c + k]; s.cu.frame[o][k] = src[k]; }
-        s.con_dist[o] = src[3 + 4 * c + 3]; s.con_pair[o] = (uint8_t)p;
+        s.con_dist[o] = src[3 + 4 * c + 3]; s.con_pair[o] = s.act_pair[a];
         make_frame(s.cu.frame[o]);
       }
     }

@@ -134,25 +134,25 @@ UR3E_HD void controller(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Re
 }
 
 // ---------------------------------------------------------------- observation / reward / termination
-struct ContactFlags { int grasp_count; int table_hit; };
+struct ContactFlags { int grasp_count; int table_hit; int self_hit; };
 
 template <typename Real, typename D>
 UR3E_HD ContactFlags contact_flags(const DevModel<Real>& m, const EnvCfg<Real>& c, const Arena<Real, D>& s) {
-  // gym_utils.py:108-128 (distinct pad bodies touching the mug) and :174-201 (gripper subtree vs table)
+  // gym_utils.py:108-128 (distinct pad bodies touching the mug), :174-201 (gripper subtree vs table) and :146-172 (two bodies of
+  // the robot_base subtree that are not both in the gripper subtree); bodies as in the loaded model (GeomFlag)
+  (void)c;
   int f = 0;
   if constexpr (D::HAS_CONTACT) {
     WARP_FOR(k, s.ncon) {
-      int p = s.con_pair[k], b1 = m.geom_body[m.pair_g1[p]], b2 = m.geom_body[m.pair_g2[p]];
-      bool mug = b1 == c.body_mug || b2 == c.body_mug;
-      if (mug && (b1 == c.body_lpad || b2 == c.body_lpad)) f |= 1;
-      if (mug && (b1 == c.body_rpad || b2 == c.body_rpad)) f |= 2;
-      bool tab = b1 == c.body_table || b2 == c.body_table;
-      int other = b1 == c.body_table ? b2 : b1;
-      if (tab && ((c.gripper_mask >> other) & 1u)) f |= 4;
+      const int p = s.con_pair[k], f1 = m.geom_flags[m.pair_g1[p]], f2 = m.geom_flags[m.pair_g2[p]], any = f1 | f2;
+      if ((any & GF_MUG) && (any & GF_LPAD)) f |= 1;
+      if ((any & GF_MUG) && (any & GF_RPAD)) f |= 2;
+      if (((f1 & GF_TABLE) && (f2 & GF_GRIPPER)) || ((f2 & GF_TABLE) && (f1 & GF_GRIPPER))) f |= 4;
+      if ((f1 & GF_ARM) && (f2 & GF_ARM) && !((f1 & GF_GRIPPER) && (f2 & GF_GRIPPER))) f |= 8;
     }
   }
   f = warp_or(f);
-  ContactFlags r; r.grasp_count = (f & 1) + ((f >> 1) & 1); r.table_hit = (f >> 2) & 1;
+  ContactFlags r; r.grasp_count = (f & 1) + ((f >> 1) & 1); r.table_hit = (f >> 2) & 1; r.self_hit = (f >> 3) & 1;
   return r;
 }
 
@@ -206,7 +206,7 @@ template <typename Real> UR3E_HD Real reward_v2(const Real* o, Real grip) {
 }
 
 // reward_v0: ur3e_env.py:256-393
-template <typename Real> UR3E_HD Real reward_v0(const Real* o, Real grip, Real half_h, int table_hit, int toppled) {
+template <typename Real> UR3E_HD Real reward_v0(const Real* o, Real grip, Real half_h, int table_hit, int toppled, int self_hit) {
   Real gs = o[9];
   Real top = o[5] + half_h, bot = o[5] - half_h, pad_top = o[12] - top, g2c = o[2] - o[5];
   Real hx = o[0] - o[3], hy = o[1] - o[4], herr = Num<Real>::sqrt(hx * hx + hy * hy);
@@ -223,7 +223,7 @@ template <typename Real> UR3E_HD Real reward_v0(const Real* o, Real grip, Real h
   if (dplace < Real(0.05) && valid) placement += 40;
   Real dh = o[5] - o[2] + Real(0.5);
   Real danger = rmin(Real(0), Real(-100000000000.0) * dh * dh * dh);
-  Real pen = Real(-25) * table_hit + Real(-8) * toppled + Real(-4) * rmax(Real(0), pad_top) + danger;   // self-collision needs mesh geoms (never fires here)
+  Real pen = Real(-40) * self_hit + Real(-25) * table_hit + Real(-8) * toppled + Real(-4) * rmax(Real(0), pad_top) + danger;   // ur3e_env.py:339-345
   Real action_r = Real(700.5) * grip * ready, bonus = Real(1700.5) * g2 * ready * Num<Real>::tanh(10 * grip);
   return descent + align + grasp + lift + placement + action_r + bonus + pen;
 }
@@ -242,16 +242,18 @@ UR3E_HD StepOut<Real> reward_done(const DevModel<Real>& m, const EnvCfg<Real>& c
     Real dpick = norm3(o[0] - o[3], o[1] - o[4], o[2] - o[5]);
     int toppled = o[5] <= c.topple_z;
     if (dpick > 1) { r.terminated = 1; r.reason = ST_TERM_REACH; }
+    else if (cf.self_hit) { r.terminated = 1; r.reason = ST_TERM_COLLISION; }
     else if (toppled) { r.terminated = 1; r.reason = ST_TERM_TOPPLE; }
     if (t >= c.max_steps) r.truncated = 1;
     if (norm3(o[3] - o[6], o[4] - o[7], o[5] - o[8]) < Real(0.05)) { r.terminated = 1; r.reward += 50; r.reason = ST_SUCCESS; }
   } else if (c.term_kind == TERM_V0) {
     // ur3e_env.py:178-194, 397-462: checks use t before the increment
     int toppled = o[5] <= c.topple_z;
-    r.reward = reward_v0(o, act[c.act_dim - 1], c.mug_size[2], cf.table_hit, toppled);
+    r.reward = reward_v0(o, act[c.act_dim - 1], c.mug_size[2], cf.table_hit, toppled, cf.self_hit);
     Real dpick = norm3(o[0] - o[3], o[1] - o[4], o[2] - o[5]), dplace = norm3(o[3] - o[6], o[4] - o[7], o[5] - o[8]);
     if (dplace < Real(0.005)) { r.terminated = 1; r.reason = ST_SUCCESS; }
     else if (dpick > 1) { r.terminated = 1; r.reason = ST_TERM_REACH; }
+    else if (cf.self_hit) { r.terminated = 1; r.reason = ST_TERM_COLLISION; }
     else if (toppled) { r.terminated = 1; r.reason = ST_TERM_TOPPLE; }
     if (t >= c.max_steps) r.truncated = 1;
     t += 1;

@@ -512,30 +512,39 @@ HostModel load_mjcf(const std::string& path) {
     int b1 = B.gbody[g1], b2 = B.gbody[g2];
     int a = g1, b = g2, condim; V fr, sr, si; double margin, gap;
     auto key = std::make_pair(g1, g2);
-    if (expl.count(key)) {
-      const Attr& at = expl[key]; a = expl_order[key].first; b = expl_order[key].second;
-      condim = (int)num(at, "condim", 3); fr = floats(at, "friction", 5, {1, 1, 0.005, 0.0001, 0.0001});
-      sr = floats(at, "solref", 2, kSolref); si = floats(at, "solimp", 5, kSolimp); margin = num(at, "margin", 0); gap = num(at, "gap", 0);
-    } else {
+    const bool is_expl = expl.count(key) != 0;
+    if (!is_expl) {
       int w1 = weldid[b1], w2 = weldid[b2];
       if (w1 == w2) continue;
       if (!((B.gcontype[g1] & B.gconaff[g2]) || (B.gcontype[g2] & B.gconaff[g1]))) continue;
       int pw1 = w1 != 0 ? weldid[B.bparent[w1]] : -1, pw2 = w2 != 0 ? weldid[B.bparent[w2]] : -1;
       if (w1 != 0 && w2 != 0 && (pw1 == w2 || pw2 == w1)) continue;
       if (excl.count({std::min(b1, b2), std::max(b1, b2)})) continue;
-      if (B.gprio[g1] != B.gprio[g2]) {
-        int gw = B.gprio[g1] > B.gprio[g2] ? g1 : g2;
-        fr = {B.gfriction[3 * gw], B.gfriction[3 * gw], B.gfriction[3 * gw + 1], B.gfriction[3 * gw + 2], B.gfriction[3 * gw + 2]};
-        sr = {B.gsolref[2 * gw], B.gsolref[2 * gw + 1]}; si.assign(B.gsolimp.begin() + 5 * gw, B.gsolimp.begin() + 5 * gw + 5); condim = B.gcondim[gw];
-      } else {
-        double f[3]; for (int k = 0; k < 3; ++k) f[k] = std::max(B.gfriction[3 * g1 + k], B.gfriction[3 * g2 + k]);
-        fr = {f[0], f[0], f[1], f[2], f[2]};
-        double s1 = B.gsolmix[g1], s2 = B.gsolmix[g2], mix = (s1 + s2) > kMinVal ? s1 / (s1 + s2) : 0.5;
-        for (int k = 0; k < 2; ++k) sr.push_back(mix * B.gsolref[2 * g1 + k] + (1 - mix) * B.gsolref[2 * g2 + k]);
-        for (int k = 0; k < 5; ++k) si.push_back(mix * B.gsolimp[5 * g1 + k] + (1 - mix) * B.gsolimp[5 * g2 + k]);
-        condim = std::max(B.gcondim[g1], B.gcondim[g2]);
-      }
-      margin = std::max(B.gmargin[g1], B.gmargin[g2]); gap = std::max(B.ggap[g1], B.ggap[g2]);
+    }
+    // contact parameters mixed from the two geoms (priority, else max friction / solmix-weighted solref, solimp)
+    if (B.gprio[g1] != B.gprio[g2]) {
+      int gw = B.gprio[g1] > B.gprio[g2] ? g1 : g2;
+      fr = {B.gfriction[3 * gw], B.gfriction[3 * gw], B.gfriction[3 * gw + 1], B.gfriction[3 * gw + 2], B.gfriction[3 * gw + 2]};
+      sr = {B.gsolref[2 * gw], B.gsolref[2 * gw + 1]}; si.assign(B.gsolimp.begin() + 5 * gw, B.gsolimp.begin() + 5 * gw + 5); condim = B.gcondim[gw];
+    } else {
+      double f[3]; for (int k = 0; k < 3; ++k) f[k] = std::max(B.gfriction[3 * g1 + k], B.gfriction[3 * g2 + k]);
+      fr = {f[0], f[0], f[1], f[2], f[2]};
+      double s1 = B.gsolmix[g1], s2 = B.gsolmix[g2], mix = (s1 + s2) > kMinVal ? s1 / (s1 + s2) : 0.5;
+      for (int k = 0; k < 2; ++k) sr.push_back(mix * B.gsolref[2 * g1 + k] + (1 - mix) * B.gsolref[2 * g2 + k]);
+      for (int k = 0; k < 5; ++k) si.push_back(mix * B.gsolimp[5 * g1 + k] + (1 - mix) * B.gsolimp[5 * g2 + k]);
+      condim = std::max(B.gcondim[g1], B.gcondim[g2]);
+    }
+    margin = std::max(B.gmargin[g1], B.gmargin[g2]); gap = std::max(B.ggap[g1], B.ggap[g2]);
+    if (is_expl) {
+      // explicit <pair>: always tested (no filtering); attributes it leaves out are inferred from its geoms as above
+      // (MuJoCo's compiler, mjCPair::Compile), the ones it sets override
+      const Attr& at = expl[key]; a = expl_order[key].first; b = expl_order[key].second;
+      if (has(at, "condim")) condim = (int)num(at, "condim", 3);
+      if (has(at, "friction")) fr = floats(at, "friction", 5, fr);
+      if (has(at, "solref")) sr = floats(at, "solref", 2, sr);
+      if (has(at, "solimp")) si = floats(at, "solimp", 5, si);
+      if (has(at, "margin")) margin = num(at, "margin", 0);
+      if (has(at, "gap")) gap = num(at, "gap", 0);
     }
     if (condim != 3) fail("only condim=3 contacts are supported");
     if (B.gtype[b] == GEOM_PLANE) std::swap(a, b);  // plane first
