@@ -200,9 +200,13 @@ __global__ void stats_kernel(EnvState<Real, D>* st, long long n, double* out, in
   }
 }
 
-template <typename Real, typename D, typename DL = D>
+// D: generic size class of the model family; DL: lite twin (small caps, exact-fit) or D; DX: exact-fit twin of D with the same caps, or D
+template <typename Real, typename D, typename DL = D, typename DX = D>
 struct Batch : BatchBase {
   static constexpr bool HAS_LITE = !std::is_same<D, DL>::value;
+  static constexpr bool HAS_X = !std::is_same<D, DX>::value;
+  static_assert(sizeof(Arena<Real, D>) == sizeof(Arena<Real, DX>) && sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DX>), "the exact-fit twin must share the generic class's layout");
+  bool full_exact = false;   // the loaded model has exactly DX's sizes: the full tier runs the exact-fit kernel
   static_assert(sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DL>), "lite and full size classes must share the record layout");
   int *d_ovf_count = nullptr, *d_ovf_list = nullptr, *h_ovf = nullptr; cudaEvent_t ovf_ev = nullptr, order_ev = nullptr; bool ovf_pending = false; int h_ovf_seen = 0;
   cudaStream_t last_stream = nullptr;   // stream of the latest asynchronous call on this handle (step_host orders itself after it)
@@ -319,6 +323,14 @@ struct Batch : BatchBase {
       if (m.nlevel != SM::NLEVEL || m.nM != SM::NM || m.nfl != SM::NFL || m.neq != SM::NEQ || m.nsite != SM::NSITE || m.ndeq != SM::NDEQ || m.nej != SM::NEJ ||
           (m.has_damping != 0) != SM::DAMPING || m.split != DL::SPLIT) single_tier = true;
     }
+    if constexpr (HAS_X) {
+      using SM = StaticModel<DX>;
+      full_exact = m.nv == DX::NV && m.nbody == DX::NB && m.nq == DX::NQ && m.nu == DX::NU && m.ngeom == DX::NG && m.npair == DX::NPAIR &&
+                   m.nlevel == SM::NLEVEL && m.nM == SM::NM && m.nfl == SM::NFL && m.neq == SM::NEQ && m.nsite == SM::NSITE && m.ndeq == SM::NDEQ && m.nej == SM::NEJ &&
+                   (m.has_damping != 0) == SM::DAMPING && m.split == DX::SPLIT;
+      CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DX>() * warps_per_block<Real, DX>())));
+      CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DX>() * warps_per_block<Real, DX>())));
+    }
     if (cfg.lite_max_contacts > 0 && cfg.lite_max_contacts < DL::MAXCON) lite_cap_con = cfg.lite_max_contacts;
     if (cfg.lite_max_rows > 0 && cfg.lite_max_rows < DL::MAXEFC) lite_cap_efc = cfg.lite_max_rows;
     size_t smem = arena_stride<Real, D>() * WPB;
@@ -340,8 +352,11 @@ struct Batch : BatchBase {
       lite_wpb = WL; lite_arena_bytes = (int)arena_stride<Real, DL>(); lite_regs = fl.numRegs;
       CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lite_blocks_per_sm, step_kernel<Real, DL>, WL * 32, arena_stride<Real, DL>() * WL));
     }
-    { cudaFuncAttributes fs; CUDA_OK(cudaFuncGetAttributes(&fs, step_kernel<Real, D>)); regs = fs.numRegs;
-      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, step_kernel<Real, D>, WPB * 32, smem)); }
+    { cudaFuncAttributes fs;
+      if (full_exact) CUDA_OK(cudaFuncGetAttributes(&fs, step_kernel<Real, DX>)); else CUDA_OK(cudaFuncGetAttributes(&fs, step_kernel<Real, D>));
+      regs = fs.numRegs;
+      if (full_exact) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, step_kernel<Real, DX>, WPB * 32, smem));
+      else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, step_kernel<Real, D>, WPB * 32, smem)); }
     CUDA_OK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     return 0;
   }
@@ -373,7 +388,7 @@ struct Batch : BatchBase {
   int get_event(cudaEvent_t* e) { if (!ev_pool.empty()) { *e = ev_pool.back(); ev_pool.pop_back(); return 0; } CUDA_OK(cudaEventCreate(e)); return 0; }
   template <typename DD> int launch_step(KArgs<Real>& a, cudaStream_t s, unsigned blocks) {
     constexpr int W = warps_per_block<Real, DD>();
-    Timed t{nullptr, nullptr, (HAS_LITE && std::is_same<DD, DL>::value) ? 0 : 1};
+    Timed t{nullptr, nullptr, (HAS_LITE && std::is_same<DD, DL>::value) ? 0 : 1};   // 0 = lite tier, 1 = full tier (generic or exact-fit)
     if (timing) { if (int rc = get_event(&t.a)) return rc; if (int rc = get_event(&t.b)) return rc; CUDA_OK(cudaEventRecord(t.a, s)); }
     if (a.sens) step_kernel<Real, DD, true><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
     else step_kernel<Real, DD><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
@@ -390,6 +405,10 @@ struct Batch : BatchBase {
   }
   // Steps the environments [lo, lo + cnt) (buffers are the whole batch's; `slot` selects the overflow counter, so that
   // ranges stepped concurrently on different streams do not share one).
+  int launch_full(KArgs<Real>& a, cudaStream_t s, unsigned blocks) {
+    if constexpr (HAS_X) { if (full_exact) return launch_step<DX>(a, s, blocks); }
+    return launch_step<D>(a, s, blocks);
+  }
   int step_range(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc, void* fobs, cudaStream_t s, long long lo, long long cnt, int slot) {
     KArgs<Real> a = base; a.op = OP_STEP; a.seed = seed;
     a.n = cnt; a.st = d_state + lo; a.env_base = base.env_base + (unsigned long long)lo;
@@ -398,7 +417,7 @@ struct Batch : BatchBase {
     a.sens = sens_dev ? (Real*)sens_dev + lo * NSENSOR : nullptr;
     constexpr int WF = warps_per_block<Real, D>();
     const unsigned full_blocks = (unsigned)((cnt + WF - 1) / WF);
-    if constexpr (!HAS_LITE) return launch_step<D>(a, s, full_blocks);
+    if constexpr (!HAS_LITE) return launch_full(a, s, full_blocks);
     else {
       // Two tiers.  The lite size class (small row / contact caps -> small arena -> more resident warps) steps every environment
       // except those whose record says they recently needed the full size class (EnvState::tier); these, and the few that turn
@@ -409,7 +428,7 @@ struct Batch : BatchBase {
       a.lite_maxcon = lite_cap_con; a.lite_maxefc = lite_cap_efc; a.ovf_stat = d_ovf_count + HOST_CHUNKS + slot;
       if (single_tier) {   // testing aid: the full size class alone, every environment
         a.lite_maxcon = 0;
-        if (int rc = launch_step<D>(a, s, full_blocks)) return rc;
+        if (int rc = launch_full(a, s, full_blocks)) return rc;
         ++full_steps;
         return 0;
       }
@@ -429,7 +448,7 @@ struct Batch : BatchBase {
       if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
       a.list_count = counter; a.list = d_ovf_list + lo;
       unsigned tail_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;
-      if (int rc = launch_step<D>(a, s, tail_blocks)) return rc;
+      if (int rc = launch_full(a, s, tail_blocks)) return rc;
       ++lite_steps;
       if (!ovf_pending && slot == 0) {   // information only (ur3e_batch_tier_info): size of the full tier's list, read back without synchronising
         CUDA_OK(cudaMemcpyAsync(h_ovf, counter, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -528,9 +547,9 @@ struct Batch : BatchBase {
 };
 
 
-template <typename Real, typename D, typename DL = D>
+template <typename Real, typename D, typename DL = D, typename DX = D>
 std::unique_ptr<BatchBase> make_batch(const HostModel& h, const ur3e_env_config& cfg, long long n, int device) {
-  auto p = std::make_unique<Batch<Real, D, DL>>();
+  auto p = std::make_unique<Batch<Real, D, DL, DX>>();
   if (p->init(h, cfg, n, device)) return nullptr;
   return p;
 }

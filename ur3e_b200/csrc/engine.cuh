@@ -34,6 +34,7 @@ using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 12, 56>;    // assets/ur3e_2f85.xml
 using DimsGripExact = Dims<17, 14, 14, 7, 6, 12, 12, 56, 14, true>;   // the same caps, compiled for exactly ur3e_2f85.xml's sizes (float32 only)
 using DimsMain = Dims<19, 20, 21, 7, 14, 48, 24, 96, 14>;   // assets/main.xml (collidable geoms: four pad boxes, the mug, the table plane, eight link hulls)
 using DimsMainLite = Dims<19, 20, 21, 7, 14, 48, 8, 44, 14, true>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
+using DimsMainX = Dims<19, 20, 21, 7, 14, 48, 24, 96, 14, true>;      // the full caps, compiled for exactly main.xml's sizes (float32 only): the grasp tier
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 constexpr int STAGE_W = 3 + 4 * STAGE_PTS;
@@ -108,6 +109,7 @@ struct Arena {
 template <typename D> struct StaticModel { static constexpr int NLEVEL = 0, NM = 0, NFL = 0, NEQ = 0, NSITE = 0, NDEQ = 0, NEJ = 0; static constexpr bool DAMPING = false; };
 template <> struct StaticModel<DimsGripExact> { static constexpr int NLEVEL = 10, NM = 81, NFL = 6, NEQ = 3, NSITE = 1, NDEQ = 6, NEJ = 1; static constexpr bool DAMPING = true; };
 template <> struct StaticModel<DimsMainLite> { static constexpr int NLEVEL = 10, NM = 102, NFL = 6, NEQ = 3, NSITE = 4, NDEQ = 6, NEJ = 1; static constexpr bool DAMPING = true; };
+template <> struct StaticModel<DimsMainX> : StaticModel<DimsMainLite> {};
 #define UR3E_MODEL_CONST(fn, STATIC, field) \
   template <typename D, typename Real> UR3E_HD auto fn(const DevModel<Real>& m) { if constexpr (D::EXACT) return StaticModel<D>::STATIC; else return m.field; }
 UR3E_MODEL_CONST(nlevel_, NLEVEL, nlevel) UR3E_MODEL_CONST(nM_, NM, nM) UR3E_MODEL_CONST(nfl_, NFL, nfl) UR3E_MODEL_CONST(neq_, NEQ, neq)
