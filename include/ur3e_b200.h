@@ -104,11 +104,14 @@ int ur3e_batch_debug_forward(ur3e_batch* b, int64_t env, double* M_nvnv, double*
 /* kernels launched by this batch so far; bytes of shared memory per environment; environments resident per SM */
 int64_t ur3e_batch_launch_count(const ur3e_batch* b);
 int ur3e_batch_kernel_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t* warps_per_block, int32_t* blocks_per_sm, int32_t* regs_per_thread);
-/* two-tier stepping of the float32 main.xml batch: out8 = lite arena bytes, lite warps/block, lite blocks/SM,
+/* tiered stepping of the float32 main.xml batch: out8 = lite arena bytes, lite warps/block, lite blocks/SM,
  * lite registers, two-tier steps, full-only steps (single_tier), environments the full tier stepped at the last observed step, 0; all zero
  * when the batch has a single size class.  Which tier steps an environment is decided per environment on the device (its own
  * recent contact / row counts), so trajectories do not depend on the batch size, the world size or host timing. */
 int ur3e_batch_tier_info(const ur3e_batch* b, int64_t* out8);
+/* the grasp tier of the float32 main.xml batch (16 contacts / 68 rows, between the lite and the generic size class): shared memory per
+ * environment, warps per block, registers per thread; zeros when the batch has none */
+int ur3e_batch_mid_tier_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t* warps_per_block, int32_t* regs_per_thread);
 /* Measurement aid (bench.py's roofline): while enabled, every step-kernel launch is bracketed by a cudaEvent pair on the launching
  * stream.  ur3e_batch_kernel_times synchronises and returns {lite-tier kernel ms, lite-tier launches, full-tier kernel ms, full-tier
  * launches} accumulated since the timing was enabled (a batch with one size class reports it as the full tier). */

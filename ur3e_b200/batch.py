@@ -139,6 +139,10 @@ class SimBatch:
         if t[0]:
             d["lite"] = dict(arena_bytes=int(t[0]), warps_per_block=int(t[1]), blocks_per_sm=int(t[2]), regs_per_thread=int(t[3]),
                              lite_tier_steps=int(t[4]), full_only_steps=int(t[5]), last_overflow_envs=int(t[6]))
+            mv = [C.c_int32() for _ in range(3)]
+            _lib.check(self._L.ur3e_batch_mid_tier_info(self.ptr, *[C.byref(x) for x in mv]), "ur3e_batch_mid_tier_info")
+            if mv[0].value:
+                d["grasp_tier"] = dict(arena_bytes=mv[0].value, warps_per_block=mv[1].value, regs_per_thread=mv[2].value)
         return d
 
     def kernel_timing(self, enable=True):

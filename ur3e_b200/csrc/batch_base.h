@@ -36,6 +36,7 @@ struct BatchBase {
   virtual int64_t last_overflow() const { return 0; }
   int arena_bytes = 0, blocks_per_sm = 0, regs = 0, device = 0, state_bytes = 0, wpb = 0;
   int lite_arena_bytes = 0, lite_blocks_per_sm = 0, lite_regs = 0, lite_wpb = 0;   // zero when the model has no lite size class
+  int mid_arena_bytes = 0, mid_regs = 0, mid_wpb = 0;                              // zero when the model has no grasp-tier size class
   long long n = 0;
 };
 

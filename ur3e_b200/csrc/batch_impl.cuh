@@ -139,8 +139,8 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
     if (idx >= count) return;
     const long long e = a.list ? (long long)a.list[idx] : idx;
     EnvState<Real, D>* const rec = static_cast<EnvState<Real, D>*>(a.st) + e;
-    if (a.ovf_list) {
-      // lite tier: an environment that recently needed the full size class goes straight to it (no wasted lite step)
+    if (a.ovf_list && !a.list) {
+      // lite tier: an environment that recently needed a larger size class goes straight to it (no wasted lite step)
       if (rec->tier > 0) { IF_LANE0 { const int k = atomicAdd(a.ovf_count, 1); a.ovf_list[k] = (int)e; } return; }
     }
     int4* gst = reinterpret_cast<int4*>(rec);
@@ -152,12 +152,14 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
     }
     WARP_SYNC();
     StepOut<Real> r = env_step(m, c, s, a.opt, a.act + e * c.act_dim, *a.opt_dev, SENS ? a.sens : nullptr, e);
-    if (a.ovf_list) {
-      // lite tier: this environment needed more rows / contacts than the lite arena holds; leave its stored state
-      // untouched and hand it to the full kernel (iters == 1 here, so the warp is done)
-      if (s.overflow) { IF_LANE0 { const int k = atomicAdd(a.ovf_count, 1); a.ovf_list[k] = (int)e; } return; }
-    } else if (a.lite_maxcon > 0) {
-      // full tier of a two-tier batch: keep the environment here while its steps do not fit the lite caps (+ TIER_HOLD steps)
+    if (a.ovf_list && s.overflow) {
+      // lite / grasp tier: this environment needed more rows / contacts than this size class's arena holds; leave its stored
+      // state untouched and hand it to the next tier's list
+      IF_LANE0 { const int k = atomicAdd(a.ovf_count, 1); a.ovf_list[k] = (int)e; }
+      continue;   // (no block barrier follows in this pass)
+    }
+    if (a.lite_maxcon > 0) {
+      // grasp / full tier of a tiered batch: keep the environment off the lite tier while its steps do not fit the lite caps (+ TIER_HOLD steps)
       IF_LANE0 {
         const bool big = s.max_ncon > a.lite_maxcon || s.max_nefc > a.lite_maxefc;
         s.st.tier = big ? TIER_HOLD : (s.st.tier > 0 ? s.st.tier - 1 : 0);
@@ -200,13 +202,14 @@ __global__ void stats_kernel(EnvState<Real, D>* st, long long n, double* out, in
   }
 }
 
-// D: generic size class of the model family; DL: lite twin (small caps, exact-fit) or D; DX: exact-fit twin of D with the same caps, or D
-template <typename Real, typename D, typename DL = D, typename DX = D>
+// D: generic size class of the model family; DL: lite twin (small caps, exact-fit) or D; DM: grasp-tier twin (caps between DL's and D's,
+// exact-fit) or D.  Tiers hand environments up through device-side lists: DL -> DM -> D.
+template <typename Real, typename D, typename DL = D, typename DM = D>
 struct Batch : BatchBase {
   static constexpr bool HAS_LITE = !std::is_same<D, DL>::value;
-  static constexpr bool HAS_X = !std::is_same<D, DX>::value;
-  static_assert(sizeof(Arena<Real, D>) == sizeof(Arena<Real, DX>) && sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DX>), "the exact-fit twin must share the generic class's layout");
-  bool full_exact = false;   // the loaded model has exactly DX's sizes: the full tier runs the exact-fit kernel
+  static constexpr bool HAS_MID = !std::is_same<D, DM>::value;
+  static_assert(sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DM>), "all size classes of a model must share the record layout");
+  int* d_ovf_list2 = nullptr;
   static_assert(sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DL>), "lite and full size classes must share the record layout");
   int *d_ovf_count = nullptr, *d_ovf_list = nullptr, *h_ovf = nullptr; cudaEvent_t ovf_ev = nullptr, order_ev = nullptr; bool ovf_pending = false; int h_ovf_seen = 0;
   cudaStream_t last_stream = nullptr;   // stream of the latest asynchronous call on this handle (step_host orders itself after it)
@@ -229,7 +232,7 @@ struct Batch : BatchBase {
 
   ~Batch() override {
     cudaSetDevice(device);
-    cudaFree(d_ovf_count); cudaFree(d_ovf_list); if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev); if (order_ev) cudaEventDestroy(order_ev);
+    cudaFree(d_ovf_count); cudaFree(d_ovf_list); cudaFree(d_ovf_list2); if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev); if (order_ev) cudaEventDestroy(order_ev);
     cudaFree(d_model); cudaFree(d_consts); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
     for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : ev_pool) cudaEventDestroy(e);
@@ -323,13 +326,14 @@ struct Batch : BatchBase {
       if (m.nlevel != SM::NLEVEL || m.nM != SM::NM || m.nfl != SM::NFL || m.neq != SM::NEQ || m.nsite != SM::NSITE || m.ndeq != SM::NDEQ || m.nej != SM::NEJ ||
           (m.has_damping != 0) != SM::DAMPING || m.split != DL::SPLIT) single_tier = true;
     }
-    if constexpr (HAS_X) {
-      using SM = StaticModel<DX>;
-      full_exact = m.nv == DX::NV && m.nbody == DX::NB && m.nq == DX::NQ && m.nu == DX::NU && m.ngeom == DX::NG && m.npair == DX::NPAIR &&
-                   m.nlevel == SM::NLEVEL && m.nM == SM::NM && m.nfl == SM::NFL && m.neq == SM::NEQ && m.nsite == SM::NSITE && m.ndeq == SM::NDEQ && m.nej == SM::NEJ &&
-                   (m.has_damping != 0) == SM::DAMPING && m.split == DX::SPLIT;
-      CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DX>() * warps_per_block<Real, DX>())));
-      CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DX>() * warps_per_block<Real, DX>())));
+    if constexpr (HAS_MID) {
+      static_assert(HAS_LITE && DM::EXACT, "the grasp tier sits between an exact-fit lite tier and the generic class");
+      constexpr int WM = warps_per_block<Real, DM>();
+      CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DM>() * WM)));
+      CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DM>() * WM)));
+      CUDA_OK(cudaMalloc(&d_ovf_list2, sizeof(int) * n_envs));
+      cudaFuncAttributes fm; CUDA_OK(cudaFuncGetAttributes(&fm, step_kernel<Real, DM>));
+      mid_wpb = WM; mid_arena_bytes = (int)arena_stride<Real, DM>(); mid_regs = fm.numRegs;
     }
     if (cfg.lite_max_contacts > 0 && cfg.lite_max_contacts < DL::MAXCON) lite_cap_con = cfg.lite_max_contacts;
     if (cfg.lite_max_rows > 0 && cfg.lite_max_rows < DL::MAXEFC) lite_cap_efc = cfg.lite_max_rows;
@@ -345,18 +349,15 @@ struct Batch : BatchBase {
       constexpr int WL = warps_per_block<Real, DL>();
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
-      CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int) * 2 * HOST_CHUNKS)); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
+      CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int) * 3 * HOST_CHUNKS)); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
       CUDA_OK(cudaMallocHost(&h_ovf, sizeof(int))); *h_ovf = 0;
       CUDA_OK(cudaEventCreateWithFlags(&ovf_ev, cudaEventDisableTiming));
       cudaFuncAttributes fl; CUDA_OK(cudaFuncGetAttributes(&fl, step_kernel<Real, DL>));
       lite_wpb = WL; lite_arena_bytes = (int)arena_stride<Real, DL>(); lite_regs = fl.numRegs;
       CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lite_blocks_per_sm, step_kernel<Real, DL>, WL * 32, arena_stride<Real, DL>() * WL));
     }
-    { cudaFuncAttributes fs;
-      if (full_exact) CUDA_OK(cudaFuncGetAttributes(&fs, step_kernel<Real, DX>)); else CUDA_OK(cudaFuncGetAttributes(&fs, step_kernel<Real, D>));
-      regs = fs.numRegs;
-      if (full_exact) CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, step_kernel<Real, DX>, WPB * 32, smem));
-      else CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, step_kernel<Real, D>, WPB * 32, smem)); }
+    { cudaFuncAttributes fs; CUDA_OK(cudaFuncGetAttributes(&fs, step_kernel<Real, D>)); regs = fs.numRegs;
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, step_kernel<Real, D>, WPB * 32, smem)); }
     CUDA_OK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     return 0;
   }
@@ -388,7 +389,7 @@ struct Batch : BatchBase {
   int get_event(cudaEvent_t* e) { if (!ev_pool.empty()) { *e = ev_pool.back(); ev_pool.pop_back(); return 0; } CUDA_OK(cudaEventCreate(e)); return 0; }
   template <typename DD> int launch_step(KArgs<Real>& a, cudaStream_t s, unsigned blocks) {
     constexpr int W = warps_per_block<Real, DD>();
-    Timed t{nullptr, nullptr, (HAS_LITE && std::is_same<DD, DL>::value) ? 0 : 1};   // 0 = lite tier, 1 = full tier (generic or exact-fit)
+    Timed t{nullptr, nullptr, (HAS_LITE && std::is_same<DD, DL>::value) ? 0 : 1};   // 0 = lite tier, 1 = grasp + full tiers
     if (timing) { if (int rc = get_event(&t.a)) return rc; if (int rc = get_event(&t.b)) return rc; CUDA_OK(cudaEventRecord(t.a, s)); }
     if (a.sens) step_kernel<Real, DD, true><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
     else step_kernel<Real, DD><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
@@ -405,10 +406,6 @@ struct Batch : BatchBase {
   }
   // Steps the environments [lo, lo + cnt) (buffers are the whole batch's; `slot` selects the overflow counter, so that
   // ranges stepped concurrently on different streams do not share one).
-  int launch_full(KArgs<Real>& a, cudaStream_t s, unsigned blocks) {
-    if constexpr (HAS_X) { if (full_exact) return launch_step<DX>(a, s, blocks); }
-    return launch_step<D>(a, s, blocks);
-  }
   int step_range(const void* act, void* obs, void* rew, uint8_t* term, uint8_t* trunc, void* fobs, cudaStream_t s, long long lo, long long cnt, int slot) {
     KArgs<Real> a = base; a.op = OP_STEP; a.seed = seed;
     a.n = cnt; a.st = d_state + lo; a.env_base = base.env_base + (unsigned long long)lo;
@@ -417,7 +414,7 @@ struct Batch : BatchBase {
     a.sens = sens_dev ? (Real*)sens_dev + lo * NSENSOR : nullptr;
     constexpr int WF = warps_per_block<Real, D>();
     const unsigned full_blocks = (unsigned)((cnt + WF - 1) / WF);
-    if constexpr (!HAS_LITE) return launch_full(a, s, full_blocks);
+    if constexpr (!HAS_LITE) return launch_step<D>(a, s, full_blocks);
     else {
       // Two tiers.  The lite size class (small row / contact caps -> small arena -> more resident warps) steps every environment
       // except those whose record says they recently needed the full size class (EnvState::tier); these, and the few that turn
@@ -428,7 +425,7 @@ struct Batch : BatchBase {
       a.lite_maxcon = lite_cap_con; a.lite_maxefc = lite_cap_efc; a.ovf_stat = d_ovf_count + HOST_CHUNKS + slot;
       if (single_tier) {   // testing aid: the full size class alone, every environment
         a.lite_maxcon = 0;
-        if (int rc = launch_full(a, s, full_blocks)) return rc;
+        if (int rc = launch_step<D>(a, s, full_blocks)) return rc;
         ++full_steps;
         return 0;
       }
@@ -441,14 +438,24 @@ struct Batch : BatchBase {
         ++lite_steps;
         return 0;
       }
+      int* const counter2 = d_ovf_count + 2 * HOST_CHUNKS + slot;
       CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), s));
       CUDA_OK(cudaMemsetAsync(a.ovf_stat, 0, sizeof(int), s));
       KArgs<Real> l = a;
       l.ovf_count = counter; l.ovf_list = d_ovf_list + lo; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc; l.lite_maxcon = 0; l.ovf_stat = nullptr;
       if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
-      a.list_count = counter; a.list = d_ovf_list + lo;
-      unsigned tail_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count); if (tail_blocks > full_blocks) tail_blocks = full_blocks;
-      if (int rc = launch_full(a, s, tail_blocks)) return rc;
+      unsigned tail_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count);
+      if constexpr (HAS_MID) {
+        // grasp tier: steps the lite tier's list; what exceeds its own caps goes on to a second list for the generic class
+        constexpr int WM = warps_per_block<Real, DM>();
+        const unsigned mid_blocks = (unsigned)((cnt + WM - 1) / WM);
+        CUDA_OK(cudaMemsetAsync(counter2, 0, sizeof(int), s));
+        KArgs<Real> mk = a;
+        mk.list_count = counter; mk.list = d_ovf_list + lo; mk.ovf_count = counter2; mk.ovf_list = d_ovf_list2 + lo;
+        if (int rc = launch_step<DM>(mk, s, tail_blocks < mid_blocks ? tail_blocks : mid_blocks)) return rc;
+        a.list_count = counter2; a.list = d_ovf_list2 + lo;
+      } else { a.list_count = counter; a.list = d_ovf_list + lo; }
+      if (int rc = launch_step<D>(a, s, tail_blocks < full_blocks ? tail_blocks : full_blocks)) return rc;
       ++lite_steps;
       if (!ovf_pending && slot == 0) {   // information only (ur3e_batch_tier_info): size of the full tier's list, read back without synchronising
         CUDA_OK(cudaMemcpyAsync(h_ovf, counter, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -547,9 +554,9 @@ struct Batch : BatchBase {
 };
 
 
-template <typename Real, typename D, typename DL = D, typename DX = D>
+template <typename Real, typename D, typename DL = D, typename DM = D>
 std::unique_ptr<BatchBase> make_batch(const HostModel& h, const ur3e_env_config& cfg, long long n, int device) {
-  auto p = std::make_unique<Batch<Real, D, DL, DX>>();
+  auto p = std::make_unique<Batch<Real, D, DL, DM>>();
   if (p->init(h, cfg, n, device)) return nullptr;
   return p;
 }

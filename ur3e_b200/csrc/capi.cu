@@ -100,6 +100,11 @@ int ur3e_batch_tier_info(const ur3e_batch* b, int64_t* o) {
   o[0] = b->impl->lite_arena_bytes; o[1] = b->impl->lite_wpb; o[2] = b->impl->lite_blocks_per_sm; o[3] = b->impl->lite_regs; o[4] = l; o[5] = f; o[6] = b->impl->last_overflow(); o[7] = 0;
   return 0;
 }
+int ur3e_batch_mid_tier_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t* wpb, int32_t* regs) {
+  GUARD(b);
+  if (arena_bytes) *arena_bytes = b->impl->mid_arena_bytes; if (wpb) *wpb = b->impl->mid_wpb; if (regs) *regs = b->impl->mid_regs;
+  return 0;
+}
 int ur3e_batch_kernel_timing(ur3e_batch* b, int enable) { GUARD(b); return b->impl->kernel_timing(enable); }
 int ur3e_batch_kernel_times(ur3e_batch* b, double* out4) { GUARD(b); if (!out4) return set_err("null argument"); return b->impl->kernel_times(out4); }
 int ur3e_batch_state_bytes(const ur3e_batch* b) { return (b && b->impl) ? b->impl->state_bytes : -1; }

@@ -24,7 +24,8 @@ struct Dims {
   static constexpr bool HAS_CONTACT = MAXCON_ > 0;
   static constexpr int NS = MAXSITE;
   // candidate pairs that survive the broad phase get a narrow-phase slot; more than MAXACT at once counts as an overflow
-  static constexpr int MAXACT = !HAS_CONTACT ? 1 : (NPAIR < (MAXCON_ <= 8 ? 16 : 24) ? NPAIR : (MAXCON_ <= 8 ? 16 : 24));
+  static constexpr int ACT_CAP = MAXCON_ <= 8 ? 16 : (MAXCON_ <= 16 ? 20 : 24);
+  static constexpr int MAXACT = !HAS_CONTACT ? 1 : (NPAIR < ACT_CAP ? NPAIR : ACT_CAP);
   static constexpr int NGRP = MAXEQ + (NPAIR < MAXCON ? NPAIR : MAXCON);   // one row group per connect equality / pair with contacts
   static constexpr int MAXCONNECT = 2;   // connect equalities a size class stores rows for (the 2F85 has two; checked at batch creation)
   static constexpr int MAXDENSE = HAS_CONTACT ? 3 * MAXCONNECT + 3 * MAXCON : 1;   // stored Jacobian rows
@@ -32,9 +33,9 @@ struct Dims {
 using DimsRaw = Dims<8, 6, 6, 6, 1, 0, 0, 12>;          // body counts are after fixed-body merging (merge_bodies.h)          // assets/ur3e_raw.xml
 using DimsGrip = Dims<17, 14, 14, 7, 6, 12, 12, 56>;    // assets/ur3e_2f85.xml
 using DimsGripExact = Dims<17, 14, 14, 7, 6, 12, 12, 56, 14, true>;   // the same caps, compiled for exactly ur3e_2f85.xml's sizes (float32 only)
-using DimsMain = Dims<19, 20, 21, 7, 14, 48, 24, 96, 14>;   // assets/main.xml (collidable geoms: four pad boxes, the mug, the table plane, eight link hulls)
+using DimsMain = Dims<19, 20, 21, 7, 14, 48, 24, 92, 14>;   // assets/main.xml (collidable geoms: four pad boxes, the mug, the table plane, eight link hulls)
 using DimsMainLite = Dims<19, 20, 21, 7, 14, 48, 8, 44, 14, true>;   // same model, caps for the common case (<= 8 contacts, <= 44 rows)
-using DimsMainX = Dims<19, 20, 21, 7, 14, 48, 24, 96, 14, true>;      // the full caps, compiled for exactly main.xml's sizes (float32 only): the grasp tier
+using DimsMainMid = Dims<19, 20, 21, 7, 14, 48, 16, 68, 14, true>;   // the grasp tier: both pads on the lifted mug are 16 contacts / ~62 rows (float32 only)
 
 constexpr int STAGE_PTS = 8;  // contact points a pair can emit
 constexpr int STAGE_W = 3 + 4 * STAGE_PTS;
@@ -109,7 +110,7 @@ struct Arena {
 template <typename D> struct StaticModel { static constexpr int NLEVEL = 0, NM = 0, NFL = 0, NEQ = 0, NSITE = 0, NDEQ = 0, NEJ = 0; static constexpr bool DAMPING = false; };
 template <> struct StaticModel<DimsGripExact> { static constexpr int NLEVEL = 10, NM = 81, NFL = 6, NEQ = 3, NSITE = 1, NDEQ = 6, NEJ = 1; static constexpr bool DAMPING = true; };
 template <> struct StaticModel<DimsMainLite> { static constexpr int NLEVEL = 10, NM = 102, NFL = 6, NEQ = 3, NSITE = 4, NDEQ = 6, NEJ = 1; static constexpr bool DAMPING = true; };
-template <> struct StaticModel<DimsMainX> : StaticModel<DimsMainLite> {};
+template <> struct StaticModel<DimsMainMid> : StaticModel<DimsMainLite> {};
 #define UR3E_MODEL_CONST(fn, STATIC, field) \
   template <typename D, typename Real> UR3E_HD auto fn(const DevModel<Real>& m) { if constexpr (D::EXACT) return StaticModel<D>::STATIC; else return m.field; }
 UR3E_MODEL_CONST(nlevel_, NLEVEL, nlevel) UR3E_MODEL_CONST(nM_, NM, nM) UR3E_MODEL_CONST(nfl_, NFL, nfl) UR3E_MODEL_CONST(neq_, NEQ, neq)
