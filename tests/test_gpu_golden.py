@@ -278,3 +278,37 @@ def test_f32_production_build_per_step_drift_through_contacts():
         max_ncon = max(max_ncon, st["ncon_sum"] / st["substeps"])
     assert max_ncon >= 6, max_ncon                # beyond the four mug-table contacts: the pads do press on the mug in this episode
     assert worst_p < 2e-4 and worst_v < 2e-2, (worst_p, worst_v)
+
+
+def test_batched_demo_collection_matches_oracle_loop(tmp_path):
+    """collect_demos.py:86-189 batched: every demonstration's obs / acts equal what the reference's per-step loop
+    (pid_task_ctrl -> d.ctrl -> mj_step -> get_obs) gives on the oracle for the same trajectory (float64 build, 1e-4), in both
+    action modes; the pickle keeps the reference's list-of-Trajectory layout."""
+    from oracle import envs as OE
+    from ur3e_b200 import collect_demos as CD
+    for mode in ("indirect", "direct"):
+        d = CD.collect_expert_demonstrations(3, action_mode=mode, reset_mode="stochastic", noise_mag="low", down_sample=4, seed=5, dtype=torch.float64)
+        T = d["traj"].shape[0]
+        K = (T + 3) // 4
+        assert d["obs"].shape == (3, K + 1, 24) and d["acts"].shape == (3, K, 4 if mode == "indirect" else 7)
+        obs0 = d["obs"][:, 0].cpu().numpy()
+        assert obs0[:, 4].std() > 0                                              # stochastic reset: different mug positions
+        e = 1
+        env = OE.OracleEnv(asset("main.xml"), "indirect")
+        env.reset((obs0[e, 3] - 0.29799994, obs0[e, 4] - 0.13349916))
+        traj = d["traj"][:, e].cpu().numpy()
+        worst = 0.0
+        for t in range(600):                                                     # approach and descent of demonstration 1
+            u = env.d.pid_task_ctrl(env.tcp, traj[t], OE.GAINS_MUG)
+            env.d.ctrl[:] = u; env.d.step(1)
+            if t % 4 == 0:
+                k = t // 4
+                worst = max(worst, rel(d["obs"][e, k + 1].cpu().numpy(), env.obs()))
+                want = np.hstack([traj[t, :3], u[-1]]) if mode == "indirect" else u
+                worst = max(worst, rel(d["acts"][e, k].cpu().numpy(), want, 1e-2))
+        assert worst < 1e-4, (mode, worst)
+    trs = CD.to_trajectories(d)
+    assert len(trs) == 3 and trs[0].obs.shape == (K + 1, 24) and len(trs[0]) == K and trs[0].terminal is True
+    path = str(tmp_path / "demos" / "expert.pkl")
+    assert CD.save_demos(trs, path) == 3 and CD.save_demos(trs, path, resume_collecting=True) == 6
+    assert len(CD.load_demos(path)) == 6

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libur3e_b200.so")
+LIB_PATH = os.environ.get("UR3E_B200_LIB") or os.path.join(_HERE, "libur3e_b200.so")   # the override selects a variant build (tools/canary_check.sh)
 
 F32, F64 = 0, 1
 OBJ_BODY, OBJ_JOINT, OBJ_GEOM, OBJ_SITE, OBJ_TENDON, OBJ_ACTUATOR, OBJ_KEY = 1, 3, 5, 6, 18, 19, 23
@@ -17,7 +17,7 @@ STAT_NAMES = ["episodes", "return_sum", "length_sum", "successes", "term_reach",
               "unstable_resets", "nefc_sum", "ncon_sum", "solver_iter_sum", "substeps", "overflow_steps", "pad_contact_steps", "steps"]
 MAXCON = 32
 CACHE_SIZE = 54
-NSENSOR = 21
+NSENSOR = 28
 
 
 class ModelDims(C.Structure):

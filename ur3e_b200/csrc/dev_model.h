@@ -102,7 +102,7 @@ struct EnvCfg {
   Real topple_z;           // max(size_x, size_y) of the mug box (gym_utils.py:8-17)
 };
 
-constexpr int NSENSOR = 21;  // logging record: 7 x actuatorfrc, touch right_pad1_contact, touch left_pad1_contact, tcp xpos (3), tcp xmat (9)
+constexpr int NSENSOR = 28;  // logging record: 7 x actuatorfrc, touch right_pad1_contact, touch left_pad1_contact, tcp xpos (3), tcp xmat (9), d.ctrl (7)
 constexpr int CACHE_SIZE = 3 + 9 + 36 + 6;  // tcp_pos, tcp_mat, J_arm (6x6: rows px,py,pz,rx,ry,rz), qfrc_bias[:6]
 
 }  // namespace ur3e

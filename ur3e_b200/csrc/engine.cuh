@@ -63,9 +63,21 @@ struct alignas(16) EnvState {
               // only, so which kernel steps an environment never depends on the batch size, the chunking or the host's timing.
 };
 
+// Debug build (-DUR3E_CANARY, tools/canary_check.sh): guard words between the arena's arrays, set when a warp claims its arena and checked
+// after every environment step; a clobbered word is reported with printf and counted as an unstable step.  compute-sanitizer is closed
+// on the GPU pool, so this is the memory-safety net for the phase-aliased storage below (the aliases themselves are covered by the
+// bit-exactness tests: a premature overwrite of a live alias changes results).
+#ifdef UR3E_CANARY
+#define UR3E_GUARD(n) unsigned guard##n;
+constexpr unsigned CANARY_WORD = 0xC0FFEE5Au;
+#else
+#define UR3E_GUARD(n)
+#endif
+
 template <typename Real, typename D>
 struct Arena {
   EnvState<Real, D> st;
+  UR3E_GUARD(0)
   Real qacc[D::NV], ctrl[D::NU], act_force[D::NU];
   Real xpos[D::NB][3];
   union {   // body frames are dead once the constraint rows exist; the Newton / Euler matrix reuses their storage
@@ -74,7 +86,9 @@ struct Arena {
   } fr;
   union { alignas(16) Real colbuf[1][32]; Real obs[32]; };   // solver scratch / the step's observation (written after the last solve)
   Real cdof[D::NV][6];
+  UR3E_GUARD(1)
   Real M[D::NV * (D::NV + 1) / 2];   // packed lower triangle, M(i,j) at i(i+1)/2 + j for j <= i
+  UR3E_GUARD(2)
   Real qfrc_smooth[D::NV], qfrc_bias[D::NV], qfrc_constraint[D::NV], grad[D::NV], search[D::NV], Ma[D::NV];
   union { Real Mv[D::NV]; Real dinv[D::NV]; };   // M * search (line search) / reciprocal pivots of the shared-memory factorisations (host build, tree LDL)
   Real site_xpos[D::NS][3], site_xmat[1][9] /* tcp only */, site_velp[D::NS][3];
@@ -82,7 +96,9 @@ struct Arena {
   struct { Real frame[D::MAXCON][9]; } cu;   // contact frames: normal, two tangents.  The solver keeps each contact's cone Hessian (6 values)
                                              // in the tangents' storage (frame[c] + 3); the normal survives for the touch sensors
   Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_jv[D::MAXEFC], efc_Dact[D::MAXEFC];
+  UR3E_GUARD(3)
   Real efc_force[D::MAXEFC], efc_jar[D::MAXEFC];
+  UR3E_GUARD(4)
   uint8_t con_pair[D::MAXCON], con_row[D::MAXCON];
   uint8_t efc_type[D::MAXEFC], efc_id[D::MAXEFC];
   // row groups sharing one column set (a connect equality, the joint equality, the contacts of one geom pair)
@@ -97,13 +113,25 @@ struct Arena {
   short ncon, nefc, ne, nf, nl, ngrp, overflow, solver_iter, bad, max_ncon, max_nefc, cap_con, cap_efc;
   short sum_ncon, sum_nefc, sum_iter, warn;   // accumulated over the substeps of one env step (frame_skip <= MAX_FRAME_SKIP keeps them in range)
   short coupled;   // some constraint of this substep has entries on both sides of Dims::SPLIT
+  UR3E_GUARD(5)
   union alignas(16) {
     struct { Real cinert[D::NB][10], cdof_dot[D::NV][6], cvel[D::NB][6], cfrc[D::NB][6]; } dyn;   // cinert becomes the composite inertia, cdof_dot the crb*cdof buffer
     struct { Real lmat[D::NB][9], lpos[D::NB][3]; } kin;   // kinematics only: each body's frame relative to its parent
     Real stage[D::MAXACT][STAGE_W];   // per narrow-phase slot: shared normal (3), then up to STAGE_PTS x (pos 3, dist 1)
     Real efc_J[D::MAXDENSE][D::NV];   // dense rows only
   } u;
+  UR3E_GUARD(6)
 };
+
+#ifdef UR3E_CANARY
+template <typename Real, typename D> UR3E_HD void canary_set(Arena<Real, D>& s) {
+  IF_LANE0 { s.guard0 = s.guard1 = s.guard2 = s.guard3 = s.guard4 = s.guard5 = s.guard6 = CANARY_WORD; }
+}
+template <typename Real, typename D> UR3E_HD int canary_bad(const Arena<Real, D>& s) {
+  return (s.guard0 != CANARY_WORD) | ((s.guard1 != CANARY_WORD) << 1) | ((s.guard2 != CANARY_WORD) << 2) | ((s.guard3 != CANARY_WORD) << 3) |
+         ((s.guard4 != CANARY_WORD) << 4) | ((s.guard5 != CANARY_WORD) << 5) | ((s.guard6 != CANARY_WORD) << 6);
+}
+#endif
 
 // Further model constants of an exact-fit size class (tree depth, nnz of M, friction-loss dofs, equalities, tracked sites):
 // specialised for the class, checked against the loaded model at batch creation like the Dims sizes.
@@ -799,14 +827,15 @@ UR3E_HD void make_constraint(const DevModel<Real>& m, Arena<Real, D>& s) {
       ++ngrp; row += 3;
     }
     if constexpr (D::HAS_CONTACT) {
-      int prev = -1;
+      // consecutive contacts between the same two bodies share one column set (e.g. both boxes of a pad against the mug): one group
+      int prev1 = -1, prev2 = -1;
       for (int c = 0; c < ncon; ++c) {
-        const int p = s.con_pair[c];
-        if (p != prev) {
-          const int mask = (int)(m.body_dofmask[m.geom_body[m.pair_g1[p]]] ^ m.body_dofmask[m.geom_body[m.pair_g2[p]]]);
+        const int p = s.con_pair[c], b1 = m.geom_body[m.pair_g1[p]], b2 = m.geom_body[m.pair_g2[p]];
+        if (b1 != prev1 || b2 != prev2) {
+          const int mask = (int)(m.body_dofmask[b1] ^ m.body_dofmask[b2]);
           IF_LANE0 { s.grp_row0[ngrp] = (uint8_t)(base_c + 3 * c); s.grp_nrow[ngrp] = 0; s.grp_mask[ngrp] = mask; }
           coupled |= spans(mask);
-          ++ngrp; prev = p;
+          ++ngrp; prev1 = b1; prev2 = b2;
         }
         IF_LANE0 s.grp_nrow[ngrp - 1] += 3;
       }
@@ -1296,7 +1325,7 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
 // contact normals are still in place (the cone Hessians only reuse the tangents' storage).
 template <typename Real, typename D>
 UR3E_PHASE void sensors_cold(const DevModel<Real>& m, Arena<Real, D>& s, Real* out) {
-  WARP_FOR(a, 7) out[a] = a < nu_<D>(m) ? s.act_force[a] : Real(0);
+  WARP_FOR(a, 7) { out[a] = a < nu_<D>(m) ? s.act_force[a] : Real(0); out[21 + a] = a < nu_<D>(m) ? s.ctrl[a] : Real(0); }   // [21..28): d.ctrl as the controller set it (unclamped)
   WARP_FOR(i, 12) out[9 + i] = nsite_<D>(m) > 0 ? (i < 3 ? s.site_xpos[0][i] : s.site_xmat[0][i - 3]) : Real(0);   // the tcp is the first tracked site
   Real touch[2] = {0, 0};
   if constexpr (D::HAS_CONTACT) {

@@ -293,6 +293,9 @@ template <typename Real, typename D>
 UR3E_HD StepOut<Real> env_step(const DevModel<Real>& m, const EnvCfg<Real>& c, Arena<Real, D>& s, const SolverOpts<Real>& opt, const Real* act,
                                const SolverOpts<Real>& opt_cold, Real* sens_base = nullptr, long long env = 0) {
   IF_LANE0 { s.overflow = 0; }
+#ifdef UR3E_CANARY
+  canary_set(s);
+#endif
   controller(m, c, s, act);
   // per-step counters live in the arena, not in registers: nothing but the loop counter stays live across the substep calls
   IF_LANE0 { s.max_ncon = 0; s.max_nefc = 0; s.sum_ncon = 0; s.sum_nefc = 0; s.sum_iter = 0; s.warn = 0; }
@@ -305,6 +308,9 @@ UR3E_HD StepOut<Real> env_step(const DevModel<Real>& m, const EnvCfg<Real>& c, A
     }
   }
   WARP_SYNC();
+#ifdef UR3E_CANARY
+  { const int bad = canary_bad(s); if (bad) { IF_LANE0 { printf("ur3e_b200: arena guard word clobbered (mask 0x%x, env %lld)\n", bad, env); s.warn |= 8; } } }
+#endif
   const int warn = s.warn;
   const int sn = s.sum_nefc, sc = s.sum_ncon, si = s.sum_iter;
   update_cache(m, c, s);
