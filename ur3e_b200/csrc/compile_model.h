@@ -132,6 +132,21 @@ DevModel<Real> compile_model(const HostModel& h) {
     m.geom_body[i] = gb[g]; m.geom_kind[i] = gt[g] == GEOM_PLANE ? GK_PLANE : GK_BOX; m.geom_src[i] = g;
     cp(m.geom_pos[i], gpos, 3 * g, 3); cpmat(m.geom_mat[i], gquat, 4 * g); cp(m.geom_size[i], gsize, 3 * g, 3);
     m.geom_rbound[i] = gt[g] == GEOM_PLANE ? Real(0) : (Real)std::sqrt(gsize[3 * g] * gsize[3 * g] + gsize[3 * g + 1] * gsize[3 * g + 1] + gsize[3 * g + 2] * gsize[3 * g + 2]);
+    if (gt[g] == GEOM_PLANE) {
+      // world normal of a plane: its body chain is static, so the frame is a model constant
+      req(h.I("body_weldid")[gb[g]] == 0, "plane geoms must belong to static bodies");
+      double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+      auto lmul = [&](const double* q4) {   // R <- Q R
+        double w = q4[0], x = q4[1], y = q4[2], z = q4[3], n = std::sqrt(w * w + x * x + y * y + z * z); if (n < 1e-15) { w = 1; x = y = z = 0; n = 1; } w /= n; x /= n; y /= n; z /= n;
+        const double Q[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+                             2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z};
+        double T[9]; for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) T[3 * r + c] = Q[3 * r] * R[c] + Q[3 * r + 1] * R[3 + c] + Q[3 * r + 2] * R[6 + c];
+        for (int k = 0; k < 9; ++k) R[k] = T[k];
+      };
+      lmul(&gquat[4 * g]);
+      for (int a = gb[g]; a > 0; a = par[a]) lmul(&h.D("body_quat")[4 * a]);
+      for (int k = 0; k < 3; ++k) m.geom_nrm[i][k] = (Real)R[3 * k + 2];
+    }
     return i;
   };
   req((int)keep.size() <= MAXPAIR, "too many candidate contact pairs");
@@ -143,6 +158,8 @@ DevModel<Real> compile_model(const HostModel& h) {
     cp(m.pair_solref[np], h.D("pair_solref"), 2 * p, 2); cp(m.pair_solimp[np], h.D("pair_solimp"), 5 * p, 5);
     m.pair_margin[np] = (Real)h.D("pair_margin")[p]; m.pair_includemargin[np] = (Real)(h.D("pair_margin")[p] - h.D("pair_gap")[p]);
     m.pair_invw[np] = (Real)(h.D("geom_invweight0")[pg1[p]] + h.D("geom_invweight0")[pg2[p]]);
+    m.pair_code[np] = m.pair_g1[np] | (m.pair_g2[np] << 8) | ((gt[pg1[p]] == GEOM_PLANE ? 1 : 0) << 16);
+    m.pair_rsum[np] = m.geom_rbound[m.pair_g1[np]] + m.geom_rbound[m.pair_g2[np]] + m.pair_margin[np];
     ++np;
   }
   m.npair = np; m.ngeom = ng;

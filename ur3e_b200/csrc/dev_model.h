@@ -68,6 +68,9 @@ struct DevModel {
   Real geom_pos[MAXG][3], geom_mat[MAXG][9], geom_size[MAXG][3], geom_rbound[MAXG];
   // candidate pairs (geom1 = plane for plane-box)
   int pair_g1[MAXPAIR], pair_g2[MAXPAIR], pair_src_g1[MAXPAIR], pair_src_g2[MAXPAIR];
+  int pair_code[MAXPAIR];     // broad phase: g1 | g2 << 8 | (g1 is a plane) << 16
+  Real pair_rsum[MAXPAIR];    // broad phase: bounding radius of g1 (0 for a plane) + bounding radius of g2 + margin
+  Real geom_nrm[MAXG][3];     // planes (always on static bodies): world normal
   Real pair_friction[MAXPAIR][2], pair_solref[MAXPAIR][2], pair_solimp[MAXPAIR][5], pair_margin[MAXPAIR], pair_includemargin[MAXPAIR], pair_invw[MAXPAIR];
   // equality
   int eq_kind[MAXEQ], eq_o1[MAXEQ], eq_o2[MAXEQ];

@@ -93,8 +93,12 @@ struct Arena {
   union { Real Mv[D::NV]; Real dinv[D::NV]; };   // M * search (line search) / reciprocal pivots of the shared-memory factorisations (host build, tree LDL)
   Real site_xpos[D::NS][3], site_xmat[1][9] /* tcp only */, site_velp[D::NS][3];
   Real con_pos[D::MAXCON][3], con_dist[D::MAXCON], con_mu[D::MAXCON];
-  struct { Real frame[D::MAXCON][9]; } cu;   // contact frames: normal, two tangents.  The solver keeps each contact's cone Hessian (6 values)
-                                             // in the tangents' storage (frame[c] + 3); the normal survives for the touch sensors
+  union {
+    Real frame[D::MAXCON][9];   // contact frames: normal, two tangents.  The solver keeps each contact's cone Hessian (6 values)
+                                // in the tangents' storage (frame[c] + 3); the normal survives for the touch sensors
+    Real gpos[D::NG][3];        // broad phase only (before any contact frame exists): world positions of the collidable geoms
+  } cu;
+  static_assert(D::MAXCON * 9 >= D::NG * 3 || !D::HAS_CONTACT, "geom positions alias the contact frames");
   Real efc_aref[D::MAXEFC], efc_D[D::MAXEFC], efc_jv[D::MAXEFC], efc_Dact[D::MAXEFC];
   UR3E_GUARD(3)
   Real efc_force[D::MAXEFC], efc_jar[D::MAXEFC];
@@ -633,25 +637,17 @@ UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
   if constexpr (!D::HAS_CONTACT) { s.ncon = 0; return; }
   else {
     const int np = np_<D>(m);
+    WARP_FOR(g, ng_<D>(m)) geom_world_pos(m, s, g, s.cu.gpos[g]);
+    WARP_SYNC();
     int nact = 0;
     for (int base = 0; base < np; base += 32) {
       const int cnt = np - base < 32 ? np - base : 32;
       int bits = 0;
       WARP_FOR(i, cnt) {
-        const int p = base + i, g1 = m.pair_g1[p], g2 = m.pair_g2[p];
-        const Real margin = m.pair_margin[p];
-        Real x1[3], x2[3]; geom_world_pos(m, s, g1, x1); geom_world_pos(m, s, g2, x2);
-        const Real dd[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]};
-        bool hit;
-        if (m.geom_kind[g1] == GK_PLANE) {
-          // plane normal = third column of its frame
-          const Real* R = s.fr.k.xmat[m.geom_body[g1]]; const Real* G = m.geom_mat[g1];
-          const Real nrm[3] = {R[0] * G[2] + R[1] * G[5] + R[2] * G[8], R[3] * G[2] + R[4] * G[5] + R[5] * G[8], R[6] * G[2] + R[7] * G[5] + R[8] * G[8]};
-          hit = dot3(dd, nrm) - m.geom_rbound[g2] <= margin;
-        } else {
-          const Real r = m.geom_rbound[g1] + m.geom_rbound[g2] + margin;
-          hit = dot3(dd, dd) <= r * r;
-        }
+        const int p = base + i, code = m.pair_code[p], g1 = code & 255, g2 = (code >> 8) & 255;
+        const Real* x1 = s.cu.gpos[g1]; const Real* x2 = s.cu.gpos[g2];
+        const Real dd[3] = {x2[0] - x1[0], x2[1] - x1[1], x2[2] - x1[2]}, r = m.pair_rsum[p];
+        const bool hit = (code >> 16) ? dot3(dd, m.geom_nrm[g1]) <= r : dot3(dd, dd) <= r * r;
         if (hit) bits |= (int)(1u << i);
       }
       bits = warp_or(bits);
@@ -665,8 +661,8 @@ UR3E_HD void collision(const DevModel<Real>& m, Arena<Real, D>& s) {
     WARP_FOR(a, nact) {
       const int p = s.act_pair[a], g1 = m.pair_g1[p], g2 = m.pair_g2[p];
       const Real margin = m.pair_margin[p];
-      Real x1[3], x2[3], R1[9], R2[9];
-      geom_world_pos(m, s, g1, x1); geom_world_pos(m, s, g2, x2);
+      Real R1[9], R2[9];
+      const Real x1[3] = {s.cu.gpos[g1][0], s.cu.gpos[g1][1], s.cu.gpos[g1][2]}, x2[3] = {s.cu.gpos[g2][0], s.cu.gpos[g2][1], s.cu.gpos[g2][2]};
       mat_mul3(R1, s.fr.k.xmat[m.geom_body[g1]], m.geom_mat[g1]); mat_mul3(R2, s.fr.k.xmat[m.geom_body[g2]], m.geom_mat[g2]);
       Real* st = s.u.stage[a];
       int n;
