@@ -90,8 +90,9 @@ int ur3e_batch_set_state(ur3e_batch* b, const void* qpos_dev, const void* qvel_d
  * writes, from the last mj_step of the step, [0..7) actuatorfrc (shoulder_pan .. wrist_3, fingers), [7] touch right_pad1_contact,
  * [8] touch left_pad1_contact, [9..12) d.site("tcp").xpos, [12..21) d.site("tcp").xmat (row-major) as get_task_space_state reads
  * them after mj_step, [21..28) d.ctrl as the in-kernel controller set it (the `u` of pid_task_ctrl that collect_demos.py:139-152
- * records as the "direct" expert action).  NULL detaches (the default: no cost on the step path). */
-#define UR3E_NSENSOR 28
+ * records as the "direct" expert action), [28..46) the six <torque> site sensors of assets/main.xml:384-391 (shoulder_pan .. wrist_3,
+ * 3 values each: interaction torque between the link and its parent at the site, in the site frame).  NULL detaches (the default: no cost on the step path). */
+#define UR3E_NSENSOR 46
 int ur3e_batch_set_sensor_buffer(ur3e_batch* b, void* sensors_dev);
 /* episode statistics + solver counters since the last reset of the counters: 16 doubles (see UR3E_STAT_*) summed over the batch */
 int ur3e_batch_stats(ur3e_batch* b, double* stats16_dev, int reset_counters, void* stream);

@@ -413,6 +413,10 @@ def load_mjcf(path):
     m["exclude"] = excl
     m["pair_candidates"] = _collision_pairs(m, excl, pairs)
 
+    # torque sensors: the sites they are attached to, in sensor order
+    sn = root.find("sensor")
+    m["sensor_torque_site"] = i32([S["name"].index(e.get("site")) for e in sn.findall("torque")] if sn is not None else [])
+
     # keyframes
     K = dict(name=[], qpos=[], qvel=[])
     kf = root.find("keyframe")

@@ -209,6 +209,60 @@ class Data:
                     out[7 + k] += fn
         return out
 
+    def torque_sensors(self):
+        """The <torque> site sensors of main.xml:384-391 after forward()/step() (MuJoCo's mj_rnePostConstraint + mjSENS_TORQUE, restated):
+        cacc from qacc, cfrc_int = subtree sum of (I cacc + v x* I v - external wrenches from contacts and connect equalities), torque
+        moved from the tree's reference point to the site and rotated into the site frame.  [n_sensors, 3]."""
+        m = self.m; nb, nv = m.nbody, m.nv
+        par = m.py["body_parentid"]; root = m.py["body_rootid"]; dofbody = m.py["dof_bodyid"]; gb = m.py["geom_bodyid"]
+        cin = self.arr("cinert").reshape(nb, 10); cvel = self.arr("cvel").reshape(nb, 6); cdof = self.arr("cdof").reshape(nv, 6); cdd = self.arr("cdof_dot").reshape(nv, 6)
+        com = self.arr("subtree_com").reshape(nb, 3); xpos = self.arr("xpos").reshape(nb, 3); xmat = self.arr("xmat").reshape(nb, 3, 3)
+        qacc, qvel, f = self.arr("qacc"), self.arr("qvel"), self.arr("efc_force")
+
+        def mul_inert(i, v):
+            I = np.array([[i[0], i[3], i[4]], [i[3], i[1], i[5]], [i[4], i[5], i[2]]]); h = i[6:9]; mass = i[9]
+            return np.hstack([I @ v[:3] + np.cross(h, v[3:]), mass * v[3:] - np.cross(h, v[:3])])
+
+        cacc = np.zeros((nb, 6)); cacc[0, 3:] = -np.asarray(m.py["opt"]["gravity"], dtype=float)
+        cfrc = np.zeros((nb, 6))
+        for b in range(1, nb):
+            cacc[b] = cacc[par[b]]
+            for d in range(nv):
+                if dofbody[d] == b:
+                    cacc[b] = cacc[b] + cdd[d] * qvel[d] + cdof[d] * qacc[d]
+            Iv = mul_inert(cin[b], cvel[b])
+            cfrc[b] = mul_inert(cin[b], cacc[b]) + np.hstack([np.cross(cvel[b, :3], Iv[:3]) + np.cross(cvel[b, 3:], Iv[3:]), np.cross(cvel[b, :3], Iv[3:])])
+
+        def ext(b, p, F, sign):
+            if b > 0:
+                cfrc[b, :3] -= sign * np.cross(p - com[root[b]], F); cfrc[b, 3:] -= sign * F
+        for c in self.contacts():
+            if c.efc_address < 0:
+                continue
+            fr = np.array(c.frame[:]).reshape(3, 3); F = fr.T @ f[c.efc_address:c.efc_address + 3]; p = np.array(c.pos[:])
+            ext(gb[c.geom2], p, F, 1.0); ext(gb[c.geom1], p, F, -1.0)
+        et, eid = self.arr("efc_type"), self.arr("efc_id")
+        eq = np.asarray(m.arr("eq_data")).reshape(m.neq, -1) if m.neq else np.zeros((0, 11))
+        r = 0
+        while r < self.nefc:
+            if et[r] == 0 and m.py["eq_type"][eid[r]] == 0:        # connect equality: three rows along the world axes
+                e = eid[r]; b1, b2 = m.py["eq_obj1id"][e], m.py["eq_obj2id"][e]
+                F = f[r:r + 3].copy()
+                ext(b1, xpos[b1] + xmat[b1] @ eq[e, 0:3], F, 1.0); ext(b2, xpos[b2] + xmat[b2] @ eq[e, 3:6], F, -1.0)
+                r += 3
+            else:
+                r += 1
+        for b in range(nb - 1, 0, -1):
+            if par[b] > 0:
+                cfrc[par[b]] += cfrc[b]
+        sx = self.arr("site_xpos").reshape(-1, 3); sm = self.arr("site_xmat").reshape(-1, 3, 3)
+        out = []
+        for sid in m.py["sensor_torque_site"]:
+            b = m.py["site_bodyid"][sid]
+            tau = cfrc[b, :3] - np.cross(sx[sid] - com[root[b]], cfrc[b, 3:])
+            out.append(sm[sid].T @ tau)
+        return np.array(out).reshape(-1, 3)
+
     def set_state(self, qpos, qvel):
         self.arr("qpos")[:] = qpos; self.arr("qvel")[:] = qvel
 

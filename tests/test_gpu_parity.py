@@ -357,7 +357,7 @@ def test_logging_sensors_f64(assets):
     qp, qv = m.key("down"); d.reset(); d.set_state(qp, qv)
     u = np.zeros(7); u[6] = 255.0
     ut = torch.tensor(np.tile(u, (2, 1)), dtype=torch.float64, device="cuda")
-    worst_f = worst_t = worst_p = 0.0; touched = 0
+    worst_f = worst_t = worst_p = worst_q = 0.0; touched = 0
     for k in range(700):
         if k % 20 == 0:                     # re-seed both sides from the oracle state (contact-rich: 1e-4 per step)
             q0, v0 = d.qpos.copy(), d.qvel.copy()
@@ -370,6 +370,8 @@ def test_logging_sensors_f64(assets):
         worst_t = max(worst_t, rel(got[7:9], ref[7:9], 1.0))
         tcp = m.id("site", "tcp")
         worst_p = max(worst_p, rel(got[9:12], d.site_xpos.reshape(-1, 3)[tcp]), rel(got[12:21], d.site_xmat.reshape(-1, 9)[tcp], 1.0))
+        worst_q = max(worst_q, rel(got[28:46], d.torque_sensors().ravel(), 1e-2))        # the six <torque> site sensors (main.xml:384-391)
+        assert np.array_equal(got[21:28], u)                                              # d.ctrl as the controller set it
         touched += int(ref[7] > 0.1 or ref[8] > 0.1)
         if k == 650:
             ts = U.get_task_space_state(b)[0].cpu().numpy()
@@ -379,6 +381,6 @@ def test_logging_sensors_f64(assets):
             assert np.abs(U.get_joint_space_state(b)[0, :6].cpu().numpy() - d.qpos[:6]).max() < 1e-6
             assert np.abs(U.get_jnt_torques(b)[0].cpu().numpy() - ref[:7]).max() < 1e-4
     assert touched > 100, touched           # the scenario does exercise the touch sensors
-    assert worst_f < 1e-4 and worst_t < 1e-4 and worst_p < 1e-6, (worst_f, worst_t, worst_p)
+    assert worst_f < 1e-4 and worst_t < 1e-4 and worst_p < 1e-6 and worst_q < 1e-4, (worst_f, worst_t, worst_p, worst_q)
     assert torch.equal(sens[0], sens[1])
     b.enable_sensors(False); b.step(ut)     # detached again: stepping no longer writes

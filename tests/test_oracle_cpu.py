@@ -139,3 +139,24 @@ def test_mug_rests_on_table(assets):
         d.ctrl[:6] = d.qfrc_bias[:6]; d.step(10)
     assert d.ncon >= 4 and abs(d.qpos[16] - 0.055111) < 2e-4 and np.abs(d.qvel[14:]).max() < 1e-3
     assert d.warn_bad == 0
+
+
+def test_torque_sensors_equal_holding_torque_at_rest(assets):
+    """The <torque> site sensors (reference assets/main.xml:384-391) against a statics identity: with the arm held still by gravity
+    compensation, the component of each joint's interaction torque along its own axis is the torque that holds the link, qfrc_bias[j]
+    (the sites sit at the link origins, on the joint axes: main.xml:113,119,125,131,137,143)."""
+    m = O.Model(assets + "/main.xml"); d = O.Data(m)
+    qp, qv = m.key("down"); qp[:6] += [0.2, 0.1, -0.2, 0.3, 0.1, -0.1]
+    d.set_state(qp, qv); d.forward()
+    for _ in range(1500):                      # let the gripper's springs settle while the arm is held
+        d.ctrl[:6] = d.qfrc_bias[:6]; d.step(1)
+    d.ctrl[:6] = d.qfrc_bias[:6]; d.forward()
+    assert np.abs(d.qacc[:14]).max() < 1e-3 and np.abs(d.qvel[:14]).max() < 1e-3
+    tq = d.torque_sensors()
+    assert tq.shape == (6, 3)
+    axis = [2, 1, 1, 1, 2, 1]                  # shoulder_pan z, shoulder_lift y, elbow y, wrist_1 y, wrist_2 z, wrist_3 y (main.xml:112-142)
+    for j in range(6):
+        assert abs(tq[j, axis[j]] - d.qfrc_bias[j]) < 2e-3 * max(1.0, abs(d.qfrc_bias[j])), (j, tq[j], d.qfrc_bias[j])
+    # the wrench through the shoulder carries the whole arm: its vertical force component is the moving mass times g -- checked
+    # through the torque it produces about the base is not available here, so check the lift joint against the closed form instead:
+    # torque about the lift axis = sum over the links above of m g x (horizontal lever), i.e. qfrc_bias of that joint (already above)

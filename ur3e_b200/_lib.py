@@ -17,7 +17,7 @@ STAT_NAMES = ["episodes", "return_sum", "length_sum", "successes", "term_reach",
               "unstable_resets", "nefc_sum", "ncon_sum", "solver_iter_sum", "substeps", "overflow_steps", "pad_contact_steps", "steps"]
 MAXCON = 32
 CACHE_SIZE = 54
-NSENSOR = 28
+NSENSOR = 46
 
 
 class ModelDims(C.Structure):

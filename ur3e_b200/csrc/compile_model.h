@@ -185,6 +185,11 @@ DevModel<Real> compile_model(const HostModel& h) {
   }
   // main.xml has all four; ur3e_2f85.xml lacks handle_site: track tcp only there unless the prefix continues
   m.nsite = ns;
+  m.ntq = 0;
+  if (h.arr.count("sensor_torque_site")) for (int sid : h.I("sensor_torque_site")) {
+    if (m.ntq >= MAXTQ) break;
+    m.tq_body[m.ntq] = h.I("site_bodyid")[sid]; cp(m.tq_pos[m.ntq], h.D("site_pos"), 3 * sid, 3); cpmat(m.tq_mat[m.ntq], h.D("site_quat"), 4 * sid); ++m.ntq;
+  }
   for (int a = 0; a < h.nu; ++a) {
     double gear = h.D("actuator_gear")[a];
     m.act_dof[a][0] = m.act_dof[a][1] = -1;

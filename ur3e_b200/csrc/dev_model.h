@@ -5,16 +5,25 @@
 
 namespace ur3e {
 
-constexpr int MAXB = 26;     // bodies incl. world
+// Static capacities of the device tables.  They are sized tightly for the reference scenes (after fixed-body merging): the tables are
+// read through the ~24 KB of L1 that the shared-memory carve-out leaves, so every unused slot costs cache.
+#ifndef UR3E_MAXB
+#define UR3E_MAXB 20
+#define UR3E_MAXG 14
+#define UR3E_MAXPAIR 48
+#define UR3E_MAXNM 104
+#endif
+constexpr int MAXB = UR3E_MAXB;     // bodies incl. world (main.xml merges to 19)
 constexpr int MAXV = 20;     // dofs
 constexpr int MAXQ = 21;     // generalized positions
 constexpr int MAXU = 7;      // actuators
-constexpr int MAXG = 16;     // collidable primitive geoms
-constexpr int MAXPAIR = 64;  // candidate geom pairs
+constexpr int MAXG = UR3E_MAXG;     // collidable primitive geoms (main.xml: 14)
+constexpr int MAXPAIR = UR3E_MAXPAIR;  // candidate geom pairs (main.xml: 48)
 constexpr int MAXEQ = 3;     // equality constraints
 constexpr int MAXSITE = 4;   // tracked sites (tcp, handle, pad)
-constexpr int MAXNM = 128;   // nnz of lower-triangular M
+constexpr int MAXNM = UR3E_MAXNM;   // nnz of lower-triangular M (main.xml: 102)
 constexpr int MAXKEY = 2;
+constexpr int MAXTQ = 6;     // torque sensors (main.xml: one per arm joint)
 constexpr int MAXANC = 12;    // ancestors of a dof in the dof tree
 constexpr int MAXCON = 32;   // contacts per env
 constexpr int MAXEFC = 112;  // constraint rows per env
@@ -78,6 +87,9 @@ struct DevModel {
   // tracked sites
   int site_body[MAXSITE];
   Real site_pos[MAXSITE][3], site_mat[MAXSITE][9], site_size[MAXSITE][3];
+  // torque sensors (logging only): body, and the site frame in that body
+  int ntq, tq_body[MAXTQ];
+  Real tq_pos[MAXTQ][3], tq_mat[MAXTQ][9];
   // actuators: force = gain*ctrl + b0 + b1*len + b2*vel ; moment over at most two dofs
   int act_dof[MAXU][2], act_ctrllimited[MAXU], act_forcelimited[MAXU];
   int dof_nact[MAXV], dof_act[MAXV][2]; Real dof_actcoef[MAXV][2];   // transposed transmission: the (at most two) actuators acting on each dof
@@ -105,7 +117,7 @@ struct EnvCfg {
   Real topple_z;           // max(size_x, size_y) of the mug box (gym_utils.py:8-17)
 };
 
-constexpr int NSENSOR = 28;  // logging record: 7 x actuatorfrc, touch right_pad1_contact, touch left_pad1_contact, tcp xpos (3), tcp xmat (9), d.ctrl (7)
+constexpr int NSENSOR = 46;  // logging record: 7 x actuatorfrc, touch right_pad1_contact, touch left_pad1_contact, tcp xpos (3), tcp xmat (9), d.ctrl (7), 6 x torque (3)
 constexpr int CACHE_SIZE = 3 + 9 + 36 + 6;  // tcp_pos, tcp_mat, J_arm (6x6: rows px,py,pz,rx,ry,rz), qfrc_bias[:6]
 
 }  // namespace ur3e

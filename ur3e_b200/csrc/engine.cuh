@@ -1312,6 +1312,127 @@ UR3E_HD void solve(const DevModel<Real>& m, Arena<Real, D>& s, const SolverOpts<
   WARP_SYNC();
 }
 
+// ---------------------------------------------------------------- torque site sensors (reference assets/main.xml:384-391)
+// mj_rnePostConstraint + mjSENS_TORQUE restated: body accelerations from the solver's qacc, inertial wrench of every body minus the
+// external wrenches on it (contacts, connect equalities), summed over the subtree = the wrench the parent transmits to the link;
+// its torque, moved to the site and expressed in the site frame, is the sensor value.  Cold path (only with a sensor buffer): the
+// body frames and velocities are rebuilt here, in storage that is dead after the solve (the Jacobian's).
+template <typename Real, typename D>
+UR3E_PHASE void torque_sensors_cold(const DevModel<Real>& m, Arena<Real, D>& s, Real* out) {
+  const int nb = nb_<D>(m), nv = nv_<D>(m);
+  auto& y = s.u.dyn;
+  // contact forces in world axes, taken before the frames' storage is rebuilt (tangents are recomputed from the normal: the solver keeps
+  // the cone Hessians in their place); kept in the dead colbuf-free efc_jv / efc_Dact rows: [3c..3c+3) = world force of contact c
+  if constexpr (D::HAS_CONTACT) {
+    WARP_FOR(c, s.ncon) {
+      Real f[9]; for (int k = 0; k < 3; ++k) f[k] = s.cu.frame[c][k];
+      make_frame(f);
+      const int r = s.con_row[c];
+      const Real f0 = s.efc_force[r], f1 = s.efc_force[r + 1], f2 = s.efc_force[r + 2];
+      for (int k = 0; k < 3; ++k) s.efc_jv[3 * c + k] = f[k] * f0 + f[3 + k] * f1 + f[6 + k] * f2;
+    }
+  }
+  WARP_SYNC();
+  kinematics(m, s);            // body frames, inertial frame positions, cdof (unchanged), site frames
+  // body inertias + velocities about the tree reference point, cdof_dot (as in dynamics())
+  WARP_FOR(b, nb) {
+    Real* ci = y.cinert[b];
+    if (b == 0 || m.body_lastdof[b] < 0) { for (int k = 0; k < 10; ++k) ci[k] = 0; for (int k = 0; k < 6; ++k) y.cvel[b][k] = 0; }
+    else {
+      const Real* ref = s.xpos[m.body_root[b]];
+      Real dif[3] = {s.fr.k.xipos[b][0] - ref[0], s.fr.k.xipos[b][1] - ref[1], s.fr.k.xipos[b][2] - ref[2]};
+      Real R[9]; mat_mul3(R, s.fr.k.xmat[b], m.body_imat[b]);
+      const Real* in = m.body_inertia[b]; Real mass = m.body_mass[b];
+      Real t00 = 0, t11 = 0, t22 = 0, t01 = 0, t02 = 0, t12 = 0;
+      for (int k = 0; k < 3; ++k) {
+        t00 += R[k] * in[k] * R[k]; t11 += R[3 + k] * in[k] * R[3 + k]; t22 += R[6 + k] * in[k] * R[6 + k];
+        t01 += R[k] * in[k] * R[3 + k]; t02 += R[k] * in[k] * R[6 + k]; t12 += R[3 + k] * in[k] * R[6 + k];
+      }
+      ci[0] = t00 + mass * (dif[1] * dif[1] + dif[2] * dif[2]); ci[1] = t11 + mass * (dif[0] * dif[0] + dif[2] * dif[2]);
+      ci[2] = t22 + mass * (dif[0] * dif[0] + dif[1] * dif[1]);
+      ci[3] = t01 - mass * dif[0] * dif[1]; ci[4] = t02 - mass * dif[0] * dif[2]; ci[5] = t12 - mass * dif[1] * dif[2];
+      ci[6] = mass * dif[0]; ci[7] = mass * dif[1]; ci[8] = mass * dif[2]; ci[9] = mass;
+      Real cv[6] = {0, 0, 0, 0, 0, 0};
+      for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { Real qd = s.st.qvel[d]; for (int k = 0; k < 6; ++k) cv[k] += s.cdof[d][k] * qd; }
+      for (int k = 0; k < 6; ++k) y.cvel[b][k] = cv[k];
+    }
+  }
+  WARP_SYNC();
+  WARP_FOR(d, nv) {
+    int b = m.dof_body[d], fk = m.dof_free_k[d];
+    Real* cd = y.cdof_dot[d];
+    if (fk >= 0 && fk < 3) { for (int k = 0; k < 6; ++k) cd[k] = 0; }
+    else {
+      Real vel[6];
+      for (int k = 0; k < 6; ++k) vel[k] = y.cvel[m.body_parent[b]][k];
+      if (fk >= 3) { int da = m.body_dadr[b]; for (int i = 0; i < 3; ++i) for (int k = 0; k < 6; ++k) vel[k] += s.cdof[da + i][k] * s.st.qvel[da + i]; }
+      cross_motion(cd, vel, s.cdof[d]);
+    }
+  }
+  WARP_SYNC();
+  // inertial wrench of every body at the solver's acceleration: I a + v x* I v, a = -g + sum over the chain of cdof_dot qvel + cdof qacc
+  WARP_FOR(b, nb) {
+    Real* f = y.cfrc[b];
+    if (b == 0 || m.body_lastdof[b] < 0) { for (int k = 0; k < 6; ++k) f[k] = 0; }
+    else {
+      Real a[6] = {0, 0, 0, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
+      for (int d = m.body_lastdof[b]; d >= 0; d = m.dof_parent[d]) { const Real qd = s.st.qvel[d], qa = s.qacc[d]; for (int k = 0; k < 6; ++k) a[k] += y.cdof_dot[d][k] * qd + s.cdof[d][k] * qa; }
+      Real t1[6], t2[6];
+      mul_inert(f, y.cinert[b], a);
+      mul_inert(t1, y.cinert[b], y.cvel[b]); cross_force(t2, y.cvel[b], t1);
+      for (int k = 0; k < 6; ++k) f[k] += t2[k];
+    }
+  }
+  WARP_SYNC();
+  // minus the external wrenches: contacts push geom2's body along the contact force and geom1's body against it; a connect equality
+  // pulls its first body with +f at the first anchor and its second with -f at the second (world axes)
+  auto apply = [&](int b, const Real* p, const Real* F, Real sign) {   // cfrc[b] -= sign * wrench of force F at point p
+    if (b <= 0 || m.body_lastdof[b] < 0) return;
+    const Real* ref = s.xpos[m.body_root[b]];
+    const Real r[3] = {p[0] - ref[0], p[1] - ref[1], p[2] - ref[2]}; Real t[3]; cross3(t, r, F);
+    IF_LANE0 { for (int k = 0; k < 3; ++k) { y.cfrc[b][k] -= sign * t[k]; y.cfrc[b][3 + k] -= sign * F[k]; } }
+  };
+  if constexpr (D::HAS_CONTACT) {
+    for (int c = 0; c < s.ncon; ++c) {
+      const int p = s.con_pair[c];
+      const Real F[3] = {s.efc_jv[3 * c], s.efc_jv[3 * c + 1], s.efc_jv[3 * c + 2]};
+      apply(m.geom_body[m.pair_g2[p]], s.con_pos[c], F, Real(1)); apply(m.geom_body[m.pair_g1[p]], s.con_pos[c], F, Real(-1));
+      WARP_SYNC();
+    }
+  }
+  {
+    int row = 0;
+    for (int e = 0; e < neq_<D>(m); ++e) if (m.eq_kind[e] == EK_CONNECT) {
+      const int b1 = m.eq_o1[e], b2 = m.eq_o2[e];
+      Real a1[3], a2[3], v[3];
+      mat_vec3(v, s.fr.k.xmat[b1], m.eq_data[e]); for (int k = 0; k < 3; ++k) a1[k] = s.xpos[b1][k] + v[k];
+      mat_vec3(v, s.fr.k.xmat[b2], m.eq_data[e] + 3); for (int k = 0; k < 3; ++k) a2[k] = s.xpos[b2][k] + v[k];
+      const Real F[3] = {s.efc_force[row], s.efc_force[row + 1], s.efc_force[row + 2]};
+      apply(b1, a1, F, Real(1)); apply(b2, a2, F, Real(-1));
+      WARP_SYNC();
+      row += 3;
+    }
+  }
+  // subtree sums (lane = component, serial down the parent < child order)
+  WARP_FOR(k, 6) { for (int b = nb - 1; b > 0; --b) { const int p = m.body_parent[b]; if (p > 0) y.cfrc[p][k] += y.cfrc[b][k]; } }
+  WARP_SYNC();
+  WARP_FOR(j, MAXTQ) {
+    Real* o = out + 28 + 3 * j;
+    if (j >= m.ntq) { o[0] = o[1] = o[2] = 0; }
+    else {
+      const int b = m.tq_body[j];
+      const Real* ref = s.xpos[m.body_root[b]]; const Real* f = y.cfrc[b];
+      Real sp[3], R[9], t[3];
+      mat_vec3(sp, s.fr.k.xmat[b], m.tq_pos[j]); mat_mul3(R, s.fr.k.xmat[b], m.tq_mat[j]);
+      const Real r[3] = {s.xpos[b][0] + sp[0] - ref[0], s.xpos[b][1] + sp[1] - ref[1], s.xpos[b][2] + sp[2] - ref[2]};
+      cross3(t, r, f + 3);
+      const Real tau[3] = {f[0] - t[0], f[1] - t[1], f[2] - t[2]};
+      for (int i = 0; i < 3; ++i) o[i] = R[i] * tau[0] + R[3 + i] * tau[1] + R[6 + i] * tau[2];   // R^T tau
+    }
+  }
+  WARP_SYNC();
+}
+
 // ---------------------------------------------------------------- logging sensors (reference assets/main.xml:392-408)
 // out[0..7) = actuatorfrc of the (up to seven) actuators, out[9..21) = tcp site position and orientation matrix,
 // out[7] / out[8] = touch sensors on the tracked sites 2 / 3
@@ -1361,6 +1482,7 @@ UR3E_PHASE void sensors_cold(const DevModel<Real>& m, Arena<Real, D>& s, Real* o
   const Real t0 = warp_sum(touch[0]), t1 = warp_sum(touch[1]);
   IF_LANE0 { out[7] = t0; out[8] = t1; }
   WARP_SYNC();
+  torque_sensors_cold(m, s, out);
 }
 
 // ---------------------------------------------------------------- one mj_step

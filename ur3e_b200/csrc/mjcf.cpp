@@ -556,6 +556,14 @@ HostModel load_mjcf(const std::string& path) {
   set_array(m, "pair_friction", pfric, {m.npair, 5}); set_array(m, "pair_solref", psolref, {m.npair, 2}); set_array(m, "pair_solimp", psolimp, {m.npair, 5});
   set_array(m, "pair_margin", pmargin, {m.npair}); set_array(m, "pair_gap", pgap, {m.npair});
 
+  // torque sensors (reference assets/main.xml:384-391): the sites they are attached to, in sensor order
+  std::vector<int> tqsite;
+  if (const XmlNode* sn = root->child("sensor")) for (auto& e : sn->children) if (e->tag == "torque") {
+    Attr a; for (auto& kv : e->attrs) a[kv.first] = kv.second;
+    tqsite.push_back(index_of(B.sname, str(a, "site"), "site"));
+  }
+  set_array(m, "sensor_torque_site", tqsite, {(long long)tqsite.size()});
+
   // keyframes
   std::vector<std::string> kname; V kqpos, kqvel;
   if (const XmlNode* kf = root->child("keyframe")) for (auto& e : kf->children) if (e->tag == "key") {
