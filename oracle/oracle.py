@@ -212,7 +212,8 @@ class Data:
     def torque_sensors(self):
         """The <torque> site sensors of main.xml:384-391 after forward()/step() (MuJoCo's mj_rnePostConstraint + mjSENS_TORQUE, restated):
         cacc from qacc, cfrc_int = subtree sum of (I cacc + v x* I v - external wrenches from contacts and connect equalities), torque
-        moved from the tree's reference point to the site and rotated into the site frame.  [n_sensors, 3]."""
+        moved from the tree's reference point to the site and rotated into the site frame.  [n_sensors, 3].
+        Reads qvel, so call it after forward() (MuJoCo evaluates sensors inside the forward pass, before integrating), not after step()."""
         m = self.m; nb, nv = m.nbody, m.nv
         par = m.py["body_parentid"]; root = m.py["body_rootid"]; dofbody = m.py["dof_bodyid"]; gb = m.py["geom_bodyid"]
         cin = self.arr("cinert").reshape(nb, 10); cvel = self.arr("cvel").reshape(nb, 6); cdof = self.arr("cdof").reshape(nv, 6); cdd = self.arr("cdof_dot").reshape(nv, 6)

@@ -52,6 +52,33 @@ extern "C" int hc_run(const char* xml, int use_float, const double* qpos, const 
   } catch (const std::exception& e) { std::fprintf(stderr, "hc_run: %s\n", e.what()); return -1; }
 }
 
+// forward pass at (qpos, qvel, ctrl) followed by the logging-sensor cold path: the [NSENSOR] record the step kernel writes
+template <typename Real, typename D>
+static int sensors(const HostModel& h, const double* qpos, const double* qvel, const double* ctrl, double* out) {
+  std::vector<int> bmap;
+  DevModel<Real> m = compile_model<Real>(merge_fixed_bodies(h, bmap));
+  auto s = std::make_unique<Arena<Real, D>>();
+  std::memset(s.get(), 0, sizeof(Arena<Real, D>));
+  for (int i = 0; i < h.nq; ++i) s->st.qpos[i] = (Real)qpos[i];
+  for (int i = 0; i < h.nv; ++i) s->st.qvel[i] = (Real)qvel[i];
+  for (int i = 0; i < h.nu; ++i) s->ctrl[i] = (Real)ctrl[i];
+  s->cap_con = D::MAXCON; s->cap_efc = D::MAXEFC;
+  SolverOpts<Real> opt{50, 50, (Real)1e-15, (Real)1e-14, (Real)1e-15, (Real)0};
+  forward(m, *s, opt, true);
+  Real rec[NSENSOR];
+  sensors_cold(m, *s, rec);
+  for (int i = 0; i < NSENSOR; ++i) out[i] = (double)rec[i];
+  return 0;
+}
+extern "C" int hc_sensors(const char* xml, const double* qpos, const double* qvel, const double* ctrl, double* out) {
+  try {
+    const HostModel& h = get_model(xml);
+    if (h.nv <= DimsRaw::NV && h.npair == 0) return sensors<double, DimsRaw>(h, qpos, qvel, ctrl, out);
+    if (h.nv <= DimsGrip::NV) return sensors<double, DimsGrip>(h, qpos, qvel, ctrl, out);
+    return sensors<double, DimsMain>(h, qpos, qvel, ctrl, out);
+  } catch (const std::exception& e) { std::fprintf(stderr, "hc_sensors: %s\n", e.what()); return -1; }
+}
+
 extern "C" int hc_model_dims(const char* xml, int* out) {
   try {
     const HostModel& h = get_model(xml);

@@ -363,14 +363,15 @@ def test_logging_sensors_f64(assets):
             q0, v0 = d.qpos.copy(), d.qvel.copy()
             d.set_state(q0, v0); d.arr("qacc_warmstart")[:] = 0
             b.set_state(torch.tensor(np.tile(q0, (2, 1)), device="cuda"), torch.tensor(np.tile(v0, (2, 1)), device="cuda"))
-        d.ctrl[:] = u; d.step(1)
+        d.ctrl[:] = u; d.forward(); ref_tq = d.torque_sensors().ravel()      # velocity-dependent: evaluated on the pre-integration state, like mj_step's sensors
+        d.step(1)
         b.step(ut)
         ref = d.sensors(); got = sens[0].cpu().numpy()
         worst_f = max(worst_f, rel(got[:7], ref[:7], 1e-2))
         worst_t = max(worst_t, rel(got[7:9], ref[7:9], 1.0))
         tcp = m.id("site", "tcp")
         worst_p = max(worst_p, rel(got[9:12], d.site_xpos.reshape(-1, 3)[tcp]), rel(got[12:21], d.site_xmat.reshape(-1, 9)[tcp], 1.0))
-        worst_q = max(worst_q, rel(got[28:46], d.torque_sensors().ravel(), 1e-2))        # the six <torque> site sensors (main.xml:384-391)
+        worst_q = max(worst_q, rel(got[28:46], ref_tq, 1e-2))        # the six <torque> site sensors (main.xml:384-391)
         assert np.array_equal(got[21:28], u)                                              # d.ctrl as the controller set it
         touched += int(ref[7] > 0.1 or ref[8] > 0.1)
         if k == 650:

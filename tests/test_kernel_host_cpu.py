@@ -80,3 +80,23 @@ def test_gripper_closing_contacts_pads(assets):
     r = HC.run(path, qp, qv, ctrl, np.zeros(m.nv), 600)
     assert d.ncon > 0 and r["ncon"] == d.ncon
     assert np.abs(r["qpos"] - d.qpos).max() < 1e-5     # 600 steps without re-seeding through a 2-point edge contact
+
+
+def test_logging_record_matches_oracle_f64(assets):
+    """The step kernel's cold sensor path compiled for the CPU: actuator forces, controller output and the six <torque> site sensors
+    (mj_rnePostConstraint restated) against the oracle, contact-free and with both pads and the gripper's hull pressing on the mug."""
+    path = assets + "/main.xml"
+    m = O.Model(path); d = O.Data(m)
+    qp, qv = m.key("down"); d.reset(); d.set_state(qp, qv)
+    u = np.zeros(7); u[6] = 255.0
+    seen_contact = False
+    for k in range(450):
+        d.ctrl[:] = u; d.step(1)
+        if k % 90 == 89:
+            q, v = d.qpos.copy(), d.qvel.copy()
+            o = O.Data(m); o.reset(); o.set_state(q, v); o.ctrl[:] = u; o.forward()
+            got = HC.sensors(path, q, v, u)
+            assert np.abs(got[:7] - o.sensors()[:7]).max() < 1e-9 and np.array_equal(got[21:28], u)
+            assert np.abs(got[28:46] - o.torque_sensors().ravel()).max() < 1e-9
+            seen_contact |= o.ncon > 4
+    assert seen_contact

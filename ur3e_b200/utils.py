@@ -7,6 +7,8 @@
     get_boolean_grasp_contact(env)    # [N] bool    utils/utils.py:238-240
     get_task_space_state(env)         # [N, 7]   controller_func.py:191-200: tcp xpos, tcp rotvec, grasp flag
     get_joint_space_state(env)        # [N, 7]   controller_func.py:203-211: qpos[:6], grasp flag
+    get_ctrl(env)                     # [N, 7]   d.ctrl as the fused controller set it (the `u` of pid_task_ctrl / move_j.ctrl)
+    get_torque_sensors(env)           # [N, 6, 3]  the <torque> site sensors of assets/main.xml:384-391 (shoulder_pan .. wrist_3)
 
 The sensors are the ones of the step's last mj_step (MuJoCo fills d.sensordata in the forward pass, before integrating),
 so a call after `step` returns what the reference's loops log after `mj_step`.  Environments that were auto-reset in that
@@ -33,6 +35,17 @@ def get_jnt_torques(d):
 
 
 get_joint_torques = get_jnt_torques   # the name controller/move_*.py import
+
+
+def get_ctrl(d):
+    """d.ctrl of the step's last mj_step, before MuJoCo's ctrlrange clamp (what the reference's loops store in `ctrls[t]`)."""
+    return _sensors(d)[:, 21:28]
+
+
+def get_torque_sensors(d):
+    """d.sensor("<joint>_torque").data for the six arm joints: interaction torque between each link and its parent at the joint's
+    force-torque site, in the site frame."""
+    return _sensors(d)[:, 28:46].reshape(-1, 6, 3)
 
 
 def get_grasp_contact(d):
