@@ -322,8 +322,12 @@ def main():
     import torch.distributed as dist
 
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: everything native libraries print while the job runs (NCCL's version banner comes out on
+    # fd 1 at the first collective) is sent to stderr; the real stdout is restored just before the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1); os.dup2(2, 1)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's own banner / debug lines must not share stdout with the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -427,7 +431,8 @@ def main():
                        "kernel_ms_lite_tier": res["kernel_ms_lite"], "kernel_ms_full_tier": res["kernel_ms_full"]},
             "roofline": r32, "roofline_hbm": rh, "cpu_baseline": cpu, "e2e": e2e, "workloads": extra or None,
             "gpu_launches": res["launches"], "clocks": sampler.summary()}
-    print(json.dumps(line))
+    sys.stdout.flush(); os.dup2(real_stdout, 1)
+    print(json.dumps(line)); sys.stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
