@@ -37,7 +37,9 @@ struct KArgs {
   // two-tier stepping (see Batch::step): overflow hand-off from the lite kernel to the full kernel
   int* ovf_count; int* ovf_list;         // lite tier: environments it hands to the full tier (lite caps exceeded, or EnvState::tier > 0); not stored
   const int* list_count; const int* list;  // full tier: process exactly these environments
-  int lite_maxcon, lite_maxefc;          // full tier of a two-tier batch: the lite caps, to maintain EnvState::tier
+  int lite_maxcon, lite_maxefc;          // grasp / generic tier of a tiered batch: the lite caps, to maintain EnvState::tier
+  int mid_maxcon, mid_maxefc;            // ... and the grasp tier's caps (0 = the batch has no grasp tier)
+  int* ovf2_count; int* ovf2_list;       // lite tier: environments whose record says they need the generic class go straight to this list
   int* ovf_stat;                         // full tier: counts the environments whose step did not fit the lite caps (information only)
   int cap_con, cap_efc;                  // row / contact caps of this launch (0 = the size class's own)
   long long n;
@@ -140,8 +142,16 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
     const long long e = a.list ? (long long)a.list[idx] : idx;
     EnvState<Real, D>* const rec = static_cast<EnvState<Real, D>*>(a.st) + e;
     if (a.ovf_list && !a.list) {
-      // lite tier: an environment that recently needed a larger size class goes straight to it (no wasted lite step)
-      if (rec->tier > 0) { IF_LANE0 { const int k = atomicAdd(a.ovf_count, 1); a.ovf_list[k] = (int)e; } return; }
+      // lite tier: an environment that recently needed a larger size class goes straight to it (no wasted lite step): to the grasp
+      // tier's list, or to the generic class's when it recently exceeded the grasp tier's caps too
+      const int tier = rec->tier;
+      if (tier & 0xff) {
+        IF_LANE0 {
+          if ((tier >> 8) && a.ovf2_list) { const int k = atomicAdd(a.ovf2_count, 1); a.ovf2_list[k] = (int)e; }
+          else { const int k = atomicAdd(a.ovf_count, 1); a.ovf_list[k] = (int)e; }
+        }
+        return;
+      }
     }
     int4* gst = reinterpret_cast<int4*>(rec);
     int4* sst = reinterpret_cast<int4*>(&s.st);
@@ -162,7 +172,9 @@ __global__ void __launch_bounds__(warps_per_block<Real, D>() * 32, UR3E_BLOCKS_P
       // grasp / full tier of a tiered batch: keep the environment off the lite tier while its steps do not fit the lite caps (+ TIER_HOLD steps)
       IF_LANE0 {
         const bool big = s.max_ncon > a.lite_maxcon || s.max_nefc > a.lite_maxefc;
-        s.st.tier = big ? TIER_HOLD : (s.st.tier > 0 ? s.st.tier - 1 : 0);
+        const bool big2 = a.mid_maxcon > 0 && (s.max_ncon > a.mid_maxcon || s.max_nefc > a.mid_maxefc);
+        const int h1 = s.st.tier & 0xff, h2 = s.st.tier >> 8;
+        s.st.tier = (big ? TIER_HOLD : (h1 > 0 ? h1 - 1 : 0)) | ((big2 ? TIER_HOLD : (h2 > 0 ? h2 - 1 : 0)) << 8);
         if (big && a.ovf_stat) atomicAdd(a.ovf_stat, 1);
       }
     }
@@ -209,7 +221,8 @@ struct Batch : BatchBase {
   static constexpr bool HAS_LITE = !std::is_same<D, DL>::value;
   static constexpr bool HAS_MID = !std::is_same<D, DM>::value;
   static_assert(sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DM>), "all size classes of a model must share the record layout");
-  int* d_ovf_list2 = nullptr;
+  int *d_ovf_list2 = nullptr, *d_ovf_list3 = nullptr;
+  cudaStream_t aux_stream[4] = {nullptr, nullptr, nullptr, nullptr}; cudaEvent_t fork_ev[4] = {nullptr, nullptr, nullptr, nullptr}, join_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   static_assert(sizeof(EnvState<Real, D>) == sizeof(EnvState<Real, DL>), "lite and full size classes must share the record layout");
   int *d_ovf_count = nullptr, *d_ovf_list = nullptr, *h_ovf = nullptr; cudaEvent_t ovf_ev = nullptr, order_ev = nullptr; bool ovf_pending = false; int h_ovf_seen = 0;
   cudaStream_t last_stream = nullptr;   // stream of the latest asynchronous call on this handle (step_host orders itself after it)
@@ -232,7 +245,8 @@ struct Batch : BatchBase {
 
   ~Batch() override {
     cudaSetDevice(device);
-    cudaFree(d_ovf_count); cudaFree(d_ovf_list); cudaFree(d_ovf_list2); if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev); if (order_ev) cudaEventDestroy(order_ev);
+    cudaFree(d_ovf_count); cudaFree(d_ovf_list); cudaFree(d_ovf_list2); cudaFree(d_ovf_list3);
+    for (int k = 0; k < 4; ++k) { if (aux_stream[k]) cudaStreamDestroy(aux_stream[k]); if (fork_ev[k]) cudaEventDestroy(fork_ev[k]); if (join_ev[k]) cudaEventDestroy(join_ev[k]); } if (h_ovf) cudaFreeHost(h_ovf); if (ovf_ev) cudaEventDestroy(ovf_ev); if (order_ev) cudaEventDestroy(order_ev);
     cudaFree(d_model); cudaFree(d_consts); cudaFree(d_state); cudaFree(d_act); cudaFree(d_obs); cudaFree(d_rew); cudaFree(d_term); cudaFree(d_trunc); cudaFree(d_dbg);
     for (auto& t : timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (auto e : ev_pool) cudaEventDestroy(e);
@@ -331,7 +345,7 @@ struct Batch : BatchBase {
       constexpr int WM = warps_per_block<Real, DM>();
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DM>() * WM)));
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DM>() * WM)));
-      CUDA_OK(cudaMalloc(&d_ovf_list2, sizeof(int) * n_envs));
+      CUDA_OK(cudaMalloc(&d_ovf_list2, sizeof(int) * n_envs)); CUDA_OK(cudaMalloc(&d_ovf_list3, sizeof(int) * n_envs));
       cudaFuncAttributes fm; CUDA_OK(cudaFuncGetAttributes(&fm, step_kernel<Real, DM>));
       mid_wpb = WM; mid_arena_bytes = (int)arena_stride<Real, DM>(); mid_regs = fm.numRegs;
     }
@@ -349,7 +363,7 @@ struct Batch : BatchBase {
       constexpr int WL = warps_per_block<Real, DL>();
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
       CUDA_OK(cudaFuncSetAttribute(step_kernel<Real, DL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(arena_stride<Real, DL>() * WL)));
-      CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int) * 3 * HOST_CHUNKS)); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
+      CUDA_OK(cudaMalloc(&d_ovf_count, sizeof(int) * 4 * HOST_CHUNKS)); CUDA_OK(cudaMalloc(&d_ovf_list, sizeof(int) * n_envs));
       CUDA_OK(cudaMallocHost(&h_ovf, sizeof(int))); *h_ovf = 0;
       CUDA_OK(cudaEventCreateWithFlags(&ovf_ev, cudaEventDisableTiming));
       cudaFuncAttributes fl; CUDA_OK(cudaFuncGetAttributes(&fl, step_kernel<Real, DL>));
@@ -438,23 +452,40 @@ struct Batch : BatchBase {
         ++lite_steps;
         return 0;
       }
-      int* const counter2 = d_ovf_count + 2 * HOST_CHUNKS + slot;
+      int* const counter2 = d_ovf_count + 2 * HOST_CHUNKS + slot;   // list 2: straight to the generic class (from the lite tier's routing)
+      int* const counter3 = d_ovf_count + 3 * HOST_CHUNKS + slot;   // list 3: exceeded the grasp tier's caps during this step
       CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), s));
       CUDA_OK(cudaMemsetAsync(a.ovf_stat, 0, sizeof(int), s));
+      const unsigned tail_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count);
       KArgs<Real> l = a;
       l.ovf_count = counter; l.ovf_list = d_ovf_list + lo; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc; l.lite_maxcon = 0; l.ovf_stat = nullptr;
-      if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
-      unsigned tail_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count);
       if constexpr (HAS_MID) {
-        // grasp tier: steps the lite tier's list; what exceeds its own caps goes on to a second list for the generic class
+        // Three tiers: lite -> grasp tier (list 1) -> generic class (lists 2 and 3).  The generic class's kernel takes the latency of one
+        // environment step however short its list is, so the environments known to need it (list 2, routed by the lite tier from their
+        // records) are stepped on a side stream WHILE the grasp tier steps list 1; only what the grasp tier itself could not hold
+        // (list 3, normally empty) is stepped afterwards.
         constexpr int WM = warps_per_block<Real, DM>();
         const unsigned mid_blocks = (unsigned)((cnt + WM - 1) / WM);
-        CUDA_OK(cudaMemsetAsync(counter2, 0, sizeof(int), s));
+        if (!aux_stream[slot]) {
+          CUDA_OK(cudaStreamCreateWithFlags(&aux_stream[slot], cudaStreamNonBlocking));
+          CUDA_OK(cudaEventCreateWithFlags(&fork_ev[slot], cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&join_ev[slot], cudaEventDisableTiming));
+        }
+        CUDA_OK(cudaMemsetAsync(counter2, 0, sizeof(int), s)); CUDA_OK(cudaMemsetAsync(counter3, 0, sizeof(int), s));
+        l.ovf2_count = counter2; l.ovf2_list = d_ovf_list2 + lo;
+        if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
+        a.mid_maxcon = DM::MAXCON; a.mid_maxefc = DM::MAXEFC;
+        CUDA_OK(cudaEventRecord(fork_ev[slot], s)); CUDA_OK(cudaStreamWaitEvent(aux_stream[slot], fork_ev[slot], 0));
+        KArgs<Real> f2 = a; f2.list_count = counter2; f2.list = d_ovf_list2 + lo;
+        if (int rc = launch_step<D>(f2, aux_stream[slot], tail_blocks < full_blocks ? tail_blocks : full_blocks)) return rc;
         KArgs<Real> mk = a;
-        mk.list_count = counter; mk.list = d_ovf_list + lo; mk.ovf_count = counter2; mk.ovf_list = d_ovf_list2 + lo;
+        mk.list_count = counter; mk.list = d_ovf_list + lo; mk.ovf_count = counter3; mk.ovf_list = d_ovf_list3 + lo;
         if (int rc = launch_step<DM>(mk, s, tail_blocks < mid_blocks ? tail_blocks : mid_blocks)) return rc;
-        a.list_count = counter2; a.list = d_ovf_list2 + lo;
-      } else { a.list_count = counter; a.list = d_ovf_list + lo; }
+        CUDA_OK(cudaEventRecord(join_ev[slot], aux_stream[slot])); CUDA_OK(cudaStreamWaitEvent(s, join_ev[slot], 0));
+        a.list_count = counter3; a.list = d_ovf_list3 + lo;
+      } else {
+        if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
+        a.list_count = counter; a.list = d_ovf_list + lo;
+      }
       if (int rc = launch_step<D>(a, s, tail_blocks < full_blocks ? tail_blocks : full_blocks)) return rc;
       ++lite_steps;
       if (!ovf_pending && slot == 0) {   // information only (ur3e_batch_tier_info): size of the full tier's list, read back without synchronising
