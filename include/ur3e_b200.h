@@ -115,10 +115,11 @@ int ur3e_batch_tier_info(const ur3e_batch* b, int64_t* out8);
  * environment, warps per block, registers per thread; zeros when the batch has none */
 int ur3e_batch_mid_tier_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t* warps_per_block, int32_t* regs_per_thread);
 /* Measurement aid (bench.py's roofline): while enabled, every step-kernel launch is bracketed by a cudaEvent pair on the launching
- * stream.  ur3e_batch_kernel_times synchronises and returns {lite-tier kernel ms, lite-tier launches, full-tier kernel ms, full-tier
- * launches} accumulated since the timing was enabled (a batch with one size class reports it as the full tier). */
+ * stream.  ur3e_batch_kernel_times synchronises and returns three {kernel ms, launches} pairs accumulated since the timing was enabled:
+ * the lite tier, the grasp / generic tier on the caller's stream (these two are the step's critical path; a batch with one size class
+ * reports it here), and the generic tier's launches on the side stream (they overlap the grasp tier). */
 int ur3e_batch_kernel_timing(ur3e_batch* b, int enable);
-int ur3e_batch_kernel_times(ur3e_batch* b, double* out4);
+int ur3e_batch_kernel_times(ur3e_batch* b, double* out6);
 /* bytes of the persistent per-environment record in HBM (read + written once per step) */
 int ur3e_batch_state_bytes(const ur3e_batch* b);
 

@@ -151,9 +151,9 @@ class SimBatch:
 
     def kernel_times(self):
         """{tier: (total ms, launches)} of the step kernels since kernel_timing(True); synchronises."""
-        v = (C.c_double * 4)()
+        v = (C.c_double * 6)()
         _lib.check(self._L.ur3e_batch_kernel_times(self.ptr, v), "ur3e_batch_kernel_times")
-        return {"lite": (v[0], int(v[1])), "full": (v[2], int(v[3]))}
+        return {"lite": (v[0], int(v[1])), "full": (v[2], int(v[3])), "side": (v[4], int(v[5]))}
 
     def close(self):
         if getattr(self, "ptr", None):

@@ -30,7 +30,7 @@ struct BatchBase {
   virtual int debug(long long env, double* M, double* bias, double* qacc, double* fc, int32_t* info, double* con, double* cache) = 0;
   // optional CUDA-event timing of every step-kernel launch (bench.py's roofline: the duration of the dominant kernel alone)
   virtual int kernel_timing(int enable) = 0;
-  virtual int kernel_times(double* out4) = 0;   // {lite-tier ms, lite-tier launches, full-tier ms, full-tier launches} since enabled; synchronises
+  virtual int kernel_times(double* out6) = 0;   // {ms, launches} x {lite tier, grasp / generic tier on the caller's stream, generic tier on the side stream}; synchronises
   int64_t launches = 0;
   virtual void tier_steps(int64_t* lite, int64_t* full) const { *lite = 0; *full = 0; }
   virtual int64_t last_overflow() const { return 0; }

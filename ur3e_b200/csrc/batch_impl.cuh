@@ -383,10 +383,11 @@ struct Batch : BatchBase {
   }
   // ---- optional per-launch timing (cudaEvent pairs on the launching stream)
   struct Timed { cudaEvent_t a, b; int tier; };
-  bool timing = false; std::vector<Timed> timed; std::vector<cudaEvent_t> ev_pool; double t_ms[2] = {0, 0}; long long t_n[2] = {0, 0};
+  bool timing = false; std::vector<Timed> timed; std::vector<cudaEvent_t> ev_pool; double t_ms[3] = {0, 0, 0}; long long t_n[3] = {0, 0, 0};
   int kernel_timing(int enable) override {
-    double tmp[4]; if (int rc = kernel_times(tmp)) return rc;   // drain
-    t_ms[0] = t_ms[1] = 0; t_n[0] = t_n[1] = 0; timing = enable != 0;
+    double tmp[6]; if (int rc = kernel_times(tmp)) return rc;   // drain
+    for (int k = 0; k < 3; ++k) { t_ms[k] = 0; t_n[k] = 0; }
+    timing = enable != 0;
     return 0;
   }
   int kernel_times(double* out4) override {
@@ -397,13 +398,14 @@ struct Batch : BatchBase {
       t_ms[t.tier] += ms; t_n[t.tier] += 1; ev_pool.push_back(t.a); ev_pool.push_back(t.b);
     }
     timed.clear();
-    out4[0] = t_ms[0]; out4[1] = (double)t_n[0]; out4[2] = t_ms[1]; out4[3] = (double)t_n[1];
+    for (int k = 0; k < 3; ++k) { out4[2 * k] = t_ms[k]; out4[2 * k + 1] = (double)t_n[k]; }
     return 0;
   }
   int get_event(cudaEvent_t* e) { if (!ev_pool.empty()) { *e = ev_pool.back(); ev_pool.pop_back(); return 0; } CUDA_OK(cudaEventCreate(e)); return 0; }
-  template <typename DD> int launch_step(KArgs<Real>& a, cudaStream_t s, unsigned blocks) {
+  // tclass (timing only): 0 = lite tier, 1 = grasp / generic tier on the caller's stream (the step's critical path), 2 = generic tier on the side stream
+  template <typename DD> int launch_step(KArgs<Real>& a, cudaStream_t s, unsigned blocks, int tclass = -1) {
     constexpr int W = warps_per_block<Real, DD>();
-    Timed t{nullptr, nullptr, (HAS_LITE && std::is_same<DD, DL>::value) ? 0 : 1};   // 0 = lite tier, 1 = grasp + full tiers
+    Timed t{nullptr, nullptr, tclass >= 0 ? tclass : ((HAS_LITE && std::is_same<DD, DL>::value) ? 0 : 1)};
     if (timing) { if (int rc = get_event(&t.a)) return rc; if (int rc = get_event(&t.b)) return rc; CUDA_OK(cudaEventRecord(t.a, s)); }
     if (a.sens) step_kernel<Real, DD, true><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
     else step_kernel<Real, DD><<<blocks, W * 32, arena_stride<Real, DD>() * W, s>>>(a);
@@ -476,7 +478,7 @@ struct Batch : BatchBase {
         a.mid_maxcon = DM::MAXCON; a.mid_maxefc = DM::MAXEFC;
         CUDA_OK(cudaEventRecord(fork_ev[slot], s)); CUDA_OK(cudaStreamWaitEvent(aux_stream[slot], fork_ev[slot], 0));
         KArgs<Real> f2 = a; f2.list_count = counter2; f2.list = d_ovf_list2 + lo;
-        if (int rc = launch_step<D>(f2, aux_stream[slot], tail_blocks < full_blocks ? tail_blocks : full_blocks)) return rc;
+        if (int rc = launch_step<D>(f2, aux_stream[slot], tail_blocks < full_blocks ? tail_blocks : full_blocks, 2)) return rc;
         KArgs<Real> mk = a;
         mk.list_count = counter; mk.list = d_ovf_list + lo; mk.ovf_count = counter3; mk.ovf_list = d_ovf_list3 + lo;
         if (int rc = launch_step<DM>(mk, s, tail_blocks < mid_blocks ? tail_blocks : mid_blocks)) return rc;

@@ -106,7 +106,7 @@ int ur3e_batch_mid_tier_info(const ur3e_batch* b, int32_t* arena_bytes, int32_t*
   return 0;
 }
 int ur3e_batch_kernel_timing(ur3e_batch* b, int enable) { GUARD(b); return b->impl->kernel_timing(enable); }
-int ur3e_batch_kernel_times(ur3e_batch* b, double* out4) { GUARD(b); if (!out4) return set_err("null argument"); return b->impl->kernel_times(out4); }
+int ur3e_batch_kernel_times(ur3e_batch* b, double* out6) { GUARD(b); if (!out6) return set_err("null argument"); return b->impl->kernel_times(out6); }
 int ur3e_batch_state_bytes(const ur3e_batch* b) { return (b && b->impl) ? b->impl->state_bytes : -1; }
 
 }  // extern "C"
