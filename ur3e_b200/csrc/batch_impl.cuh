@@ -62,6 +62,9 @@ template <typename Real, typename D> __host__ __device__ constexpr int warps_per
 #endif
   int per_sm = (int)((233472 - 1024 * UR3E_BLOCKS_PER_SM) / arena_stride<Real, D>());
   int w = per_sm / UR3E_BLOCKS_PER_SM;
+#ifdef UR3E_MID_MAX_WPB
+  if (D::EXACT && D::MAXCON == 16 && w > UR3E_MID_MAX_WPB) w = UR3E_MID_MAX_WPB;   // A/B: register budget of the grasp tier
+#endif
   return w > UR3E_MAX_WPB ? UR3E_MAX_WPB : (w < 1 ? 1 : w);
 }
 constexpr int DBG_DOUBLES = MAXV * MAXV + 3 * MAXV + 8 + 4 * MAXCON + CACHE_SIZE;
