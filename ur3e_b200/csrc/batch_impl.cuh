@@ -440,8 +440,9 @@ struct Batch : BatchBase {
       // out to exceed the lite caps during the step (left untouched by the lite kernel), are appended to a device-side list that
       // the full size class then steps from a resident grid.  The choice is a function of each environment's own history, made on
       // the device: no host read-back, no dependence on the batch size, the chunking of step_host, the world size or timing.
-      int* const counter = d_ovf_count + slot;
-      a.lite_maxcon = lite_cap_con; a.lite_maxefc = lite_cap_efc; a.ovf_stat = d_ovf_count + HOST_CHUNKS + slot;
+      // the four counters of a slot are adjacent (one memset): list 1, statistics, list 2, list 3
+      int* const counter = d_ovf_count + 4 * slot;
+      a.lite_maxcon = lite_cap_con; a.lite_maxefc = lite_cap_efc; a.ovf_stat = counter + 1;
       if (single_tier) {   // testing aid: the full size class alone, every environment
         a.lite_maxcon = 0;
         if (int rc = launch_step<D>(a, s, full_blocks)) return rc;
@@ -457,10 +458,9 @@ struct Batch : BatchBase {
         ++lite_steps;
         return 0;
       }
-      int* const counter2 = d_ovf_count + 2 * HOST_CHUNKS + slot;   // list 2: straight to the generic class (from the lite tier's routing)
-      int* const counter3 = d_ovf_count + 3 * HOST_CHUNKS + slot;   // list 3: exceeded the grasp tier's caps during this step
-      CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), s));
-      CUDA_OK(cudaMemsetAsync(a.ovf_stat, 0, sizeof(int), s));
+      int* const counter2 = counter + 2;   // list 2: straight to the generic class (from the lite tier's routing)
+      int* const counter3 = counter + 3;   // list 3: exceeded the grasp tier's caps during this step
+      CUDA_OK(cudaMemsetAsync(counter, 0, 4 * sizeof(int), s));
       const unsigned tail_blocks = (unsigned)(UR3E_BLOCKS_PER_SM * sm_count);
       KArgs<Real> l = a;
       l.ovf_count = counter; l.ovf_list = d_ovf_list + lo; l.cap_con = lite_cap_con; l.cap_efc = lite_cap_efc; l.lite_maxcon = 0; l.ovf_stat = nullptr;
@@ -475,7 +475,6 @@ struct Batch : BatchBase {
           CUDA_OK(cudaStreamCreateWithFlags(&aux_stream[slot], cudaStreamNonBlocking));
           CUDA_OK(cudaEventCreateWithFlags(&fork_ev[slot], cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&join_ev[slot], cudaEventDisableTiming));
         }
-        CUDA_OK(cudaMemsetAsync(counter2, 0, sizeof(int), s)); CUDA_OK(cudaMemsetAsync(counter3, 0, sizeof(int), s));
         l.ovf2_count = counter2; l.ovf2_list = d_ovf_list2 + lo;
         if (int rc = launch_step<DL>(l, s, lite_blocks)) return rc;
         a.mid_maxcon = DM::MAXCON; a.mid_maxefc = DM::MAXEFC;
