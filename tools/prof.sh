@@ -4,8 +4,9 @@
 w=$1; tag=$2; settle=${3:-}
 [ -z "$settle" ] && { case $w in rollout) settle=3000;; mug) settle=1500;; reach) settle=1000;; esac; }
 cmd="python bench.py --workload $w --settle $settle --steps 4 --warmup 3 --no-e2e --no-cpu-baseline --no-extra"
-# launches of step_kernel before the timed region: 3 per env-step on main.xml (lite + grasp + generic tier), 1 on the others
-per=3; [ "$w" = reach ] && per=1
+# launches of step_kernel before the timed region: 4 per env-step on main.xml (lite, generic tier on the side stream, grasp tier,
+# generic tier for the grasp tier's overflows), 1 on the others
+per=4; [ "$w" = reach ] && per=1
 skip=$(( (settle + 3) * per + per ))
 $cmd > gpurun_out/${tag}_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s $skip -c $per -o gpurun_out/$tag -f $cmd > gpurun_out/${tag}_ncu.log 2>&1
