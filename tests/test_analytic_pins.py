@@ -16,6 +16,13 @@ Model: tests/models/box_on_plane.xml (a physical pendulum + a 0.1 kg box on a pl
   sticking creep   on an incline below the friction angle the soft friction rows (K = 0, R_t = R_n / impratio) let the box creep at
                    v = g sin(theta) / (impratio B sum_i d_i / (1 - d_i))
   sliding          above the friction angle the box accelerates at about g (sin(theta) - mu cos(theta))   [coarse: 10 %]
+
+Model: tests/models/hinge_pins.xml (three independent unit hinges, no gravity): the joint-space rows and the affine actuator.
+
+  joint limit      a motor torque tau pushes the hinge into its stop: penetration r solving r = tau (1 - d) A_hat / (K d^2), A_hat = 1 / I
+  friction loss    tau below frictionloss: creep v = tau (1 - d0) A_hat / (d0 B) (pos = 0, so d = solimp[0]); above: acceleration (tau - F) / I
+  affine actuator  the 2F85's `general` form: equilibrium gain ctrl = -b1 q, and q = -gain ctrl / b1 again once the force range saturates
+                   transiently (damped joint)
 """
 import os
 
@@ -238,6 +245,55 @@ def test_sliding_above_friction_angle(tmp_path, Sim):
     want = G * (np.sin(theta) - 1.0 * np.cos(theta)) * 1.0
     assert abs(v[1] - want) / want < 0.10, (v[1], want)
     assert v[1] < G * np.sin(theta) * 0.5                                                        # far from frictionless (8.2 m/s)
+
+
+class _HingeGpu:
+    def __init__(self, path):
+        import torch
+        import ur3e_b200._lib as lib
+        from ur3e_b200.batch import SimBatch, env_config
+        from ur3e_b200.model import Model
+        self.torch = torch
+        self.b = SimBatch(Model(path), env_config(ctrl_mode=lib.CTRL_RAW, obs_kind=lib.OBS_STATE, obs_dim=6, act_dim=3, frame_skip=1), 1, 0, torch.float64)
+        self.b.reset()
+
+    def run(self, ctrl, n):
+        a = self.torch.tensor(np.asarray(ctrl, dtype=float)[None], device="cuda")
+        for _ in range(n):
+            obs, *_ = self.b.step(a)
+        o = obs[0].cpu().numpy()
+        return o[:3], o[3:]
+
+
+def _hinge_run(Sim, ctrl, n):
+    path = os.path.join(HERE, "models", "hinge_pins.xml")
+    if Sim is GpuSim:
+        return _HingeGpu(path).run(ctrl, n)
+    if Sim is KernelSourceSim:
+        from tests.hostcheck import build as HC
+        r = HC.run(path, np.zeros(3), np.zeros(3), np.asarray(ctrl, dtype=float), np.zeros(3), n)
+        return r["qpos"], r["qvel"]
+    m = O.Model(path); d = O.Data(m); d.reset(); d.ctrl[:] = ctrl; d.step(n)
+    return d.qpos.copy(), d.qvel.copy()
+
+
+@pytest.mark.parametrize("Sim", SIMS)
+def test_joint_limit_frictionloss_and_affine_actuator(Sim):
+    inertia, a_hat = 0.5, 2.0
+    q, v = _hinge_run(Sim, [2.0, 0.1, 10.0], 4000)
+    # joint limit: constant torque 2 against the upper stop at 0.5
+    r = 1e-4
+    for _ in range(200):
+        d = impedance(r); r = 2.0 * (1.0 - d) * a_hat / (K_REF * d * d)
+    assert abs((q[0] - 0.5) - r) < 1e-11 and abs(v[0]) < 1e-10
+    # friction loss 0.2 under torque 0.1: sticking, with the soft row's creep
+    assert abs(v[1] - 0.1 * (1.0 - DMIN) * a_hat / (DMIN * B_REF)) < 1e-12
+    # affine actuator: 0.3137255 * ctrl - 100 q - 10 qdot = 0 at rest
+    assert abs(q[2] - 0.3137255 * 10.0 / 100.0) < 1e-10 and abs(v[2]) < 1e-10
+    q, v = _hinge_run(Sim, [0.0, 0.5, 255.0], 2000)
+    assert abs(v[1] / 2.0 - (0.5 - 0.2) / inertia) < 1e-9                                        # sliding: Coulomb torque subtracted
+    assert abs(q[2] - 0.3137255 * 255.0 / 100.0) < 1e-6                                          # force range (+-5) only limits the approach
+    assert abs(q[0]) < 1e-15 and abs(v[0]) < 1e-15
 
 
 @pytest.mark.parametrize("Sim", SIMS)
