@@ -435,10 +435,10 @@ struct Batch : BatchBase {
     const unsigned full_blocks = (unsigned)((cnt + WF - 1) / WF);
     if constexpr (!HAS_LITE) return launch_step<D>(a, s, full_blocks);
     else {
-      // Two tiers.  The lite size class (small row / contact caps -> small arena -> more resident warps) steps every environment
-      // except those whose record says they recently needed the full size class (EnvState::tier); these, and the few that turn
-      // out to exceed the lite caps during the step (left untouched by the lite kernel), are appended to a device-side list that
-      // the full size class then steps from a resident grid.  The choice is a function of each environment's own history, made on
+      // Tiered stepping.  The lite size class (small row / contact caps -> small arena -> more resident warps) steps every environment
+      // except those whose record says they recently needed a larger size class (EnvState::tier); these, and the few that turn
+      // out to exceed the lite caps during the step (left untouched by the lite kernel), are appended to device-side lists that
+      // the larger size classes then step from resident grids.  The choice is a function of each environment's own history, made on
       // the device: no host read-back, no dependence on the batch size, the chunking of step_host, the world size or timing.
       // the four counters of a slot are adjacent (one memset): list 1, statistics, list 2, list 3
       int* const counter = d_ovf_count + 4 * slot;

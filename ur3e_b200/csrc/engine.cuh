@@ -80,14 +80,14 @@ struct Arena {
   UR3E_GUARD(0)
   Real qacc[D::NV], ctrl[D::NU], act_force[D::NU];
   Real xpos[D::NB][3];
-  union {   // body frames are dead once the constraint rows exist; the Newton / Euler matrix reuses their storage
+  union alignas(8) {   // body frames are dead once the constraint rows exist; the Newton / Euler matrix reuses their storage
     struct { Real xmat[D::NB][9], xipos[D::NB][3]; } k;
     struct { Real H[(D::NV + 1) * (D::NV + 2) / 2]; } n;   // augmented Newton / Euler matrix, packed lower triangle: (i,j) at i(i+1)/2 + j
   } fr;
   union { alignas(16) Real colbuf[1][32]; Real obs[32]; };   // solver scratch / the step's observation (written after the last solve)
   Real cdof[D::NV][6];
   UR3E_GUARD(1)
-  Real M[D::NV * (D::NV + 1) / 2];   // packed lower triangle, M(i,j) at i(i+1)/2 + j for j <= i
+  alignas(8) Real M[D::NV * (D::NV + 1) / 2];   // packed lower triangle, M(i,j) at i(i+1)/2 + j for j <= i
   UR3E_GUARD(2)
   Real qfrc_smooth[D::NV], qfrc_bias[D::NV], qfrc_constraint[D::NV], grad[D::NV], search[D::NV], Ma[D::NV];
   union { Real Mv[D::NV]; Real dinv[D::NV]; };   // M * search (line search) / reciprocal pivots of the shared-memory factorisations (host build, tree LDL)
@@ -445,9 +445,11 @@ UR3E_HD void dynamics(const DevModel<Real>& m, Arena<Real, D>& s) {
   WARP_SYNC();
   // composite inertias in place (lanes 0-9: one inertia component each) and subtree bias wrenches (lanes 10-15), both serial
   // down the (parent < child) body order
+  // (one loop for both: a lane walks its own array with its own stride, so the two groups of lanes do not diverge)
   WARP_FOR(k, 16) {
-    if (k < 10) { for (int b = nb - 1; b > 0; --b) { int p = m.body_parent[b]; if (p > 0) y.cinert[p][k] += y.cinert[b][k]; } }
-    else { int c = k - 10; for (int b = nb - 1; b > 0; --b) { int p = m.body_parent[b]; if (p > 0) y.cfrc[p][c] += y.cfrc[b][c]; } }
+    Real* const base = k < 10 ? &y.cinert[0][k] : &y.cfrc[0][k - 10];
+    const int stride = k < 10 ? 10 : 6;
+    for (int b = nb - 1; b > 0; --b) { const int p = m.body_parent[b]; if (p > 0) base[p * stride] += base[b * stride]; }
   }
   WARP_SYNC();
   // M: f_i = crb(body_i) cdof_i (stored over cdof_dot, which is dead) ; M_ij = cdof_j . f_i
@@ -1184,7 +1186,14 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
     // equality's squares on the diagonal (lane = dof) and the joint equality's single off-diagonal entry (lane = equality)
     {
       const int ntri = nv * (nv + 1) / 2;
-      WARP_FOR(e, ntri + nv) s.fr.n.H[e] = e < ntri ? s.M[e] : -s.grad[e - ntri];
+#if defined(__CUDA_ARCH__)
+      if constexpr (sizeof(Real) == 4 && D::EXACT && (D::NV * (D::NV + 1) / 2) % 2 == 0) {
+        // exact-fit float classes: M -> H as 64-bit copies (both arrays are 8-byte aligned: see the static_asserts below Arena), then the rhs row
+        const float2* src = reinterpret_cast<const float2*>(s.M); float2* dst = reinterpret_cast<float2*>(s.fr.n.H);
+        WARP_FOR(e, ntri / 2 + nv) { if (e < ntri / 2) dst[e] = src[e]; else s.fr.n.H[ntri + e - ntri / 2] = -s.grad[e - ntri / 2]; }
+      } else
+#endif
+      { WARP_FOR(e, ntri + nv) s.fr.n.H[e] = e < ntri ? s.M[e] : -s.grad[e - ntri]; }
       WARP_SYNC();
       WARP_FOR(i, nv + neq_<D>(m)) {
         if (i < nv) {
@@ -1215,7 +1224,10 @@ UR3E_HD int newton_iteration(const DevModel<Real>& m, Arena<Real, D>& s, const S
       WARP_FOR(e, kc * (kc + 1) / 2) {
         int pq = m.tri_ab[e], a = cols[pq >> 8], b = cols[pq & 255];
         Real h = 0;
-        if (!contact) { for (int r = r0; r < r1; ++r) h += s.efc_Dact[r] * s.u.efc_J[r][a] * s.u.efc_J[r][b]; }
+        if (!contact) {   // a connect equality: exactly three rows
+          h = s.efc_Dact[r0] * s.u.efc_J[r0][a] * s.u.efc_J[r0][b] + s.efc_Dact[r0 + 1] * s.u.efc_J[r0 + 1][a] * s.u.efc_J[r0 + 1][b] +
+              s.efc_Dact[r0 + 2] * s.u.efc_J[r0 + 2][a] * s.u.efc_J[r0 + 2][b];
+        }
         else {
           for (int r = r0; r + 2 < r1 + 0 && r + 2 < D::MAXDENSE; r += 3) {
             Real a0 = s.u.efc_J[r][a], a1 = s.u.efc_J[r + 1][a], a2 = s.u.efc_J[r + 2][a];
