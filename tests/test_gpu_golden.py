@@ -93,6 +93,27 @@ def test_pick_place_expert_succeeds_on_production_f32():
 
 
 @pytest.mark.parametrize("kind", ["v2", "v0"])
+def test_collision_predicates_vs_reference_fixture(kind):
+    """tests/golden/collision.npz: one step of the reference's own UR3eEnv2 / UR3eEnv (their get_self_collision / get_table_collision,
+    utils/gym_utils.py:146-201, run verbatim) from five injected arm poses: keyframe, two folded elbows (self-collision: both classes
+    terminate; v0's reward carries -40), pads pressed on the table and gripper base on the table (v0's -25, no termination).  float64
+    CUDA build: same flags, observation and reward within 1e-4; the episode statistics count the collision terminations."""
+    g = np.load(GOLD + "/collision.npz")
+    n = len(g[kind + "_qpos"])
+    assert list(g[kind + "_self_collision"]) == [0, 1, 1, 0, 0] and list(g[kind + "_table_collision"]) == [0, 0, 0, 1, 1]
+    env = UR3eVecEnv(IDS[kind], n, dtype=torch.float64, auto_reset=False, reset_noise=lib.NOISE_NONE)
+    env.reset()
+    env.set_state(torch.tensor(g[kind + "_qpos"], device="cuda"), torch.tensor(np.tile(g["qvel"], (n, 1)), device="cuda"))
+    obs, rew, term, trunc, _ = env.step(torch.tensor(g[kind + "_action"], device="cuda"))
+    assert [bool(x) for x in term.cpu()] == [bool(x) for x in g[kind + "_terminated"]]
+    for e in range(n):
+        assert rel(obs[e].cpu().numpy(), g[kind + "_obs"][e]) < 1e-4, e
+        assert abs(rew[e].item() - g[kind + "_reward"][e]) < 1e-4 * max(1.0, abs(g[kind + "_reward"][e])), (e, rew[e].item(), g[kind + "_reward"][e])
+    st = env.episode_stats()
+    assert st["term_collision"] == 2 and st["episodes"] == 2
+
+
+@pytest.mark.parametrize("kind", ["v2", "v0"])
 def test_folded_arm_self_collision_vs_oracle(kind):
     """box hulls stand in for the arm's collision meshes; get_self_collision (gym_utils.py:146-172) fires when the elbow
     folds the wrist onto the shoulder / upper arm: ur3e-v2 and ur3e-v0 terminate (ur3e_env2.py:244-246, ur3e_env.py:441-443), v0's

@@ -101,6 +101,41 @@ def pick_place_episode():
     return {k: np.asarray(v) for k, v in rec.items()}
 
 
+def collision_vectors():
+    """get_self_collision / get_table_collision (utils/gym_utils.py:146-201) as the reference's own env classes use them: one step of
+    UR3eEnv2 and UR3eEnv from injected arm poses -- keyframe 'down', elbow folded onto the shoulder (self-collision: both classes
+    terminate, ur3e_env2.py:244-246 / ur3e_env.py:441-443, v0's reward carries -40), tool pressed into the table (table collision: v0's
+    -25 penalty, no termination)."""
+    out = {}
+    sink = io.StringIO()
+    for name, cls_name, module in (("v2", "UR3eEnv2", "gymnasium_env.envs.ur3e_env2"), ("v0", "UR3eEnv", "gymnasium_env.envs.ur3e_env")):
+        mod = __import__(module, fromlist=[cls_name])
+        np.random.seed(1)
+        with contextlib.redirect_stdout(sink):
+            env = getattr(mod, cls_name)()
+            env.reset()
+        qp0, qv0 = gu.get_init(env.model, "deterministic", "down")
+        poses = []
+        for dq in ([0, 0, 0, 0, 0, 0], [0, 0, 1.2292, 0, 0, 0], [0, 0, 1.3292, 0, 0, 0], [0.5, 0.6, 0.0, -0.6, 0, 0], [0.5, 0.75, 0.1, -0.85, 0, 0]):
+            q = np.array(qp0, dtype=np.float64); q[:6] += dq; poses.append(q)
+        rec = dict(qpos=[], action=[], obs=[], reward=[], terminated=[], self_collision=[], table_collision=[], ncon=[])
+        for q in poses:
+            with contextlib.redirect_stdout(sink):
+                env.set_state(q, np.array(qv0, dtype=np.float64)); env.t = 0
+                o0 = env._get_obs()
+                a = np.hstack([o0[:3], 0.0])
+                rec["self_collision"].append(int(gu.get_self_collision(env.model, env.data, env.collision_cache)))
+                rec["table_collision"].append(int(gu.get_table_collision(env.model, env.data, env.collision_cache)))
+                rec["ncon"].append(int(env.data.ncon))
+                o, r, te, tr, _ = env.step(a)
+            rec["qpos"].append(q); rec["action"].append(a); rec["obs"].append(np.asarray(o, dtype=np.float64)); rec["reward"].append(float(r)); rec["terminated"].append(bool(te))
+        for k, v in rec.items():
+            out[name + "_" + k] = np.asarray(v)
+        print("collision", name, "self", rec["self_collision"], "table", rec["table_collision"], "terminated", rec["terminated"], "ncon", rec["ncon"])
+    out["qvel"] = np.array(qv0, dtype=np.float64)
+    return out
+
+
 def truncation_steps():
     """Step index (1-based) at which each reference env class first reports truncated=True under a hold-still action:
     ur3e_env2.py:89-92 increments t before the test (2500), the others test first (ur3e_env.py:183-194 -> 501,
@@ -189,6 +224,8 @@ def main():
         np.savez_compressed(os.path.join(OUT, "env_v2_pick.npz"), **rec)
         print("env_v2_pick steps", len(rec["reward"]), "sum reward %.4f" % rec["reward"].sum(), "robust-grasp steps", int(rec["obs"][:, 23].sum()), "max ncon", rec["ncon"].max(),
               "max mug z %.4f" % rec["obs"][:, 5].max(), "terminated", bool(rec["terminated"][-1]))
+    if not only or "collision" in only:
+        np.savez_compressed(os.path.join(OUT, "collision.npz"), **collision_vectors())
     if not only or "truncation" in only:
         np.savez_compressed(os.path.join(OUT, "truncation.npz"), **truncation_steps())
     if only and "controllers" not in only:
