@@ -17,6 +17,8 @@ Model: tests/models/box_on_plane.xml (a physical pendulum + a 0.1 kg box on a pl
                    v = g sin(theta) / (impratio B sum_i d_i / (1 - d_i))
   sliding          above the friction angle the box accelerates at about g (sin(theta) - mu cos(theta))   [coarse: 10 %]
 
+Model: tests/models/double_pendulum.xml: mass matrix (CRBA) and bias forces (RNE) against the textbook closed form.
+
 Model: tests/models/hinge_pins.xml (three independent unit hinges, no gravity): the joint-space rows and the affine actuator.
 
   joint limit      a motor torque tau pushes the hinge into its stop: penetration r solving r = tau (1 - d) A_hat / (K d^2), A_hat = 1 / I
@@ -245,6 +247,31 @@ def test_sliding_above_friction_angle(tmp_path, Sim):
     want = G * (np.sin(theta) - 1.0 * np.cos(theta)) * 1.0
     assert abs(v[1] - want) / want < 0.10, (v[1], want)
     assert v[1] < G * np.sin(theta) * 0.5                                                        # far from frictionless (8.2 m/s)
+
+
+@pytest.mark.parametrize("source", ["oracle", "kernel-source"])
+def test_double_pendulum_mass_matrix_and_bias_textbook(source):
+    """CRBA and RNE against the closed-form double pendulum (any robotics text): M11 = I1 + I2 + m1 lc1^2 + m2 (l1^2 + lc2^2 + 2 l1 lc2 c2),
+    M12 = I2 + m2 (lc2^2 + l1 lc2 c2), M22 = I2 + m2 lc2^2; bias = Coriolis / centrifugal (h = -m2 l1 lc2 s2) + gravity."""
+    path = os.path.join(HERE, "models", "double_pendulum.xml")
+    m1, m2, l1, lc1, lc2, I1, I2 = 2.0, 1.5, 0.5, 0.3, 0.25, 0.04, 0.02
+    rng = np.random.default_rng(4)
+    for _ in range(6):
+        q = rng.uniform(-2.5, 2.5, 2); v = rng.uniform(-3, 3, 2)
+        c2, s2 = np.cos(q[1]), np.sin(q[1])
+        M = np.array([[I1 + I2 + m1 * lc1 ** 2 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * c2), I2 + m2 * (lc2 ** 2 + l1 * lc2 * c2)],
+                      [I2 + m2 * (lc2 ** 2 + l1 * lc2 * c2), I2 + m2 * lc2 ** 2]])
+        h = -m2 * l1 * lc2 * s2
+        grav = np.array([m1 * G * lc1 * np.sin(q[0]) + m2 * G * (l1 * np.sin(q[0]) + lc2 * np.sin(q[0] + q[1])), m2 * G * lc2 * np.sin(q[0] + q[1])])
+        bias = np.array([h * (2 * v[0] * v[1] + v[1] ** 2), -h * v[0] ** 2]) + grav
+        if source == "oracle":
+            mo = O.Model(path); d = O.Data(mo); d.reset(); d.set_state(q, v); d.forward()
+            gotM, gotb = d.fullM(), np.asarray(d.qfrc_bias)
+        else:
+            from tests.hostcheck import build as HC
+            r = HC.run(path, q, v, np.zeros(2), np.zeros(2), 0)
+            gotM, gotb = r["M"], r["bias"]
+        assert np.abs(gotM - M).max() < 1e-12 and np.abs(gotb - bias).max() < 1e-11, (gotM, M, gotb, bias)
 
 
 class _HingeGpu:
