@@ -385,3 +385,30 @@ def test_logging_sensors_f64(assets):
     assert worst_f < 1e-4 and worst_t < 1e-4 and worst_p < 1e-6 and worst_q < 1e-4, (worst_f, worst_t, worst_p, worst_q)
     assert torch.equal(sens[0], sens[1])
     b.enable_sensors(False); b.step(ut)     # detached again: stepping no longer writes
+
+
+def test_long_random_rollout_is_stable_f32(assets):
+    """Soak: 6 000 env-steps (12 000 mj_steps) of U(action_space) actions on 4 096 production (float32) environments with auto-reset,
+    i.e. every environment runs through truncation twice: observations stay finite, the bad-state guard (mj_checkPos / Vel / Acc,
+    the reference's MUJOCO_LOG.TXT lists 20 such events) never fires, nothing overflows the largest size class, and the episode
+    counters are consistent."""
+    from ur3e_b200 import presets
+    n = 4096
+    m = Model(assets + "/main.xml")
+    _, kw, lo, hi = presets.ENV_SPECS["gymnasium_env/ur3e-v2"]
+    b = SimBatch(m, presets.make_config(m, kw, auto_reset=1), n, 0, torch.float32)
+    b.reset(seed=3)
+    lo_t, hi_t = torch.tensor(lo, device="cuda", dtype=torch.float32), torch.tensor(hi, device="cuda", dtype=torch.float32)
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    acts = [(lo_t + (hi_t - lo_t) * torch.rand(n, 4, device="cuda", generator=g)).contiguous() for _ in range(64)]
+    bad = torch.zeros((), device="cuda")
+    for k in range(6000):
+        obs, rew, term, trunc = b.step(acts[k % 64], want_final_obs=False)
+        if k % 50 == 0:
+            bad += (~torch.isfinite(obs)).sum() + (~torch.isfinite(rew)).sum()
+    st = b.stats_dict()
+    assert bad.item() == 0
+    assert st["unstable_resets"] == 0 and st["overflow_steps"] == 0
+    assert st["steps"] == n * 6000 and st["substeps"] == 2 * n * 6000
+    assert st["truncations"] >= 2 * n * 0.5 and st["episodes"] >= st["truncations"]
+    assert st["episodes"] == st["truncations"] + st["successes"] + st["term_reach"] + st["term_toppled"] + st["term_collision"]
